@@ -1,0 +1,213 @@
+/*
+ * mvf_b200.h -- C ABI of libmvf_b200.so: the drop-in boundary for the brute-force scan that
+ * thegenem0/metrovector's examples/similarity_search.rs performs on the CPU.
+ *
+ * The reference is a Rust library with no FFI of its own; its "API" for this path is the set of
+ * public reader methods plus the example's free function `find_top_k_similar`.  Every entry
+ * point below names the reference interface it replaces (paths relative to the reference
+ * repository root).  The Rust `search` module a maintainer would add binds exactly these symbols
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no C++ or torch types cross this line.
+ *
+ * Conventions
+ *   - every function returns an int status (mvf_status); 0 = OK.  1..10 are the variants of
+ *     `MvfError` in declaration order (src/errors.rs:8-40); 11 = CUDA, 12 = NCCL.
+ *   - mvf_last_error() returns the thread-local message of the last failing call on this
+ *     thread, formatted like the reference's Display strings (src/errors.rs:9-39).
+ *   - no exception or abort crosses the ABI.
+ *   - handles are opaque.  mvf_space* and row pointers borrow from their mvf_file and die with
+ *     it (src/vectors/vector_space.rs:34-39).  mvf_gpu_space* owns its HBM copy and outlives
+ *     the file it was uploaded from.
+ *   - file/space handles are immutable and thread-safe (src/reader.rs:284-289); searches on one
+ *     mvf_gpu are serialised by the caller (one stream + scratch per engine).
+ */
+#ifndef MVF_B200_H
+#define MVF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVF_API __attribute__((visibility("default")))
+
+/* src/errors.rs:8-40, in declaration order, then ours */
+typedef enum mvf_status {
+    MVF_OK = 0,
+    MVF_ERR_IO = 1,
+    MVF_ERR_INVALID_FORMAT = 2,
+    MVF_ERR_UNSUPPORTED_VERSION = 3,
+    MVF_ERR_VECTOR_SPACE_NOT_FOUND = 4,
+    MVF_ERR_INDEX_OUT_OF_BOUNDS = 5,
+    MVF_ERR_DIMENSION_MISMATCH = 6,
+    MVF_ERR_INVALID_VECTOR_TYPE = 7,
+    MVF_ERR_CORRUPTED_DATA = 8,
+    MVF_ERR_EXTENSION = 9,
+    MVF_ERR_BUILD = 10,
+    MVF_ERR_CUDA = 11,
+    MVF_ERR_NCCL = 12
+} mvf_status;
+
+/* schema/types.fbs:3-11 */
+typedef enum mvf_data_type {
+    MVF_FLOAT32 = 0, MVF_FLOAT16 = 1, MVF_INT8 = 2, MVF_UINT8 = 3,
+    MVF_UINT32 = 4, MVF_UINT64 = 5, MVF_STRING_REF = 6
+} mvf_data_type;
+/* schema/types.fbs:14-17 */
+typedef enum mvf_vector_type { MVF_DENSE = 0, MVF_SPARSE = 1 } mvf_vector_type;
+/* schema/types.fbs:19-25; README.md:160-164 spells InnerProduct "Dot" and L2 "Euclidean" */
+typedef enum mvf_distance_metric {
+    MVF_L2 = 0, MVF_INNER_PRODUCT = 1, MVF_DOT = 1, MVF_COSINE = 2, MVF_CUSTOM = 255,
+    MVF_METRIC_SPACE_DEFAULT = -1
+} mvf_distance_metric;
+
+typedef struct mvf_file mvf_file;           /* MvfReader / "MvfFile"   src/reader.rs:27-31   */
+typedef struct mvf_space mvf_space;         /* VectorSpace<'a>         src/vectors/vector_space.rs:34-39 */
+typedef struct mvf_builder mvf_builder;     /* MvfBuilder              src/builder.rs:93-98  */
+typedef struct mvf_gpu mvf_gpu;             /* one engine = one process on one B200 (new) */
+typedef struct mvf_gpu_space mvf_gpu_space; /* HBM-resident shard of one vector space (new) */
+
+MVF_API const char* mvf_last_error(void);
+MVF_API const char* mvf_version_string(void);
+
+/* ---------------------------------------------------------------- reader (src/reader.rs) -- */
+/* MvfReader::open, src/reader.rs:45-79 (README.md:97 spells it MvfFile::open) */
+MVF_API int mvf_file_open(const char* path, mvf_file** out);
+MVF_API void mvf_file_close(mvf_file* f);
+/* MvfReader::version, src/reader.rs:82 */
+MVF_API int mvf_file_version(const mvf_file* f, uint16_t* out);
+/* MvfReader::num_vector_spaces, src/reader.rs:87 */
+MVF_API int mvf_file_num_vector_spaces(const mvf_file* f, size_t* out);
+/* MvfReader::vector_space_names, src/reader.rs:92-98 (i-th name; pointer valid while file open) */
+MVF_API int mvf_file_vector_space_name(const mvf_file* f, size_t i, const char** out);
+/* MvfReader::file_size, src/reader.rs:122 */
+MVF_API int mvf_file_size(const mvf_file* f, uint64_t* out);
+/* MvfReader::has_metadata, src/reader.rs:127 */
+MVF_API int mvf_file_has_metadata(const mvf_file* f, int* out);
+/* MvfReader::metadata_column_names, src/reader.rs:132-143 */
+MVF_API int mvf_file_num_metadata_columns(const mvf_file* f, size_t* out);
+MVF_API int mvf_file_metadata_column_name(const mvf_file* f, size_t i, const char** out);
+/* MvfReader::validate, src/reader.rs:149-162 */
+MVF_API int mvf_file_validate(const mvf_file* f);
+/* the finished intent of MvfReader::validate_with_checksum, src/reader.rs:172-221 (CRC-32/IEEE
+ * of every block with a non-zero checksum, offsets taken relative to the start magic) */
+MVF_API int mvf_file_validate_with_checksum(const mvf_file* f);
+/* MvfReader::vector_space, src/reader.rs:104-119 */
+MVF_API int mvf_file_vector_space(const mvf_file* f, const char* name, mvf_space** out);
+MVF_API void mvf_space_release(mvf_space* s);
+
+/* ---------------------------------------- space view (src/vectors/vector_space.rs:62-89) -- */
+MVF_API int mvf_space_name(const mvf_space* s, const char** out);
+MVF_API int mvf_space_dimension(const mvf_space* s, uint32_t* out);
+MVF_API int mvf_space_total_vectors(const mvf_space* s, uint64_t* out);
+MVF_API int mvf_space_vector_type(const mvf_space* s, int* out);
+MVF_API int mvf_space_distance_metric(const mvf_space* s, int* out);
+MVF_API int mvf_space_data_type(const mvf_space* s, int* out);
+/* VectorSpace::get_vector + Vector::as_bytes: src/vectors/vector_space.rs:101-142,
+ * src/vectors/vector.rs:61-63.  Zero-copy pointer into the mapping. */
+MVF_API int mvf_space_get_vector(const mvf_space* s, uint64_t index, const void** ptr, size_t* nbytes);
+/* get_vector + Vector::as_f32: src/vectors/vector.rs:71-92 (Int8/UInt8 -> MVF_ERR_BUILD) */
+MVF_API int mvf_space_get_vector_f32(const mvf_space* s, uint64_t index, float* out, size_t cap);
+/* VectorSpace::map_vector_range: src/vectors/vector_space.rs:155-188 */
+MVF_API int mvf_space_map_vector_range(const mvf_space* s, uint64_t start, uint64_t count,
+                                       const void** ptr, size_t* nbytes);
+/* rows the reference scan `for i in 0..space.total_vectors()` can actually visit:
+ * min(total_vectors, block.size / (dimension*elem_size)) -- see DESIGN.md "f16 total_vectors" */
+MVF_API int mvf_space_scannable_vectors(const mvf_space* s, uint64_t* out);
+
+/* ------------------------------------------------ writer (src/builder.rs, src/io.rs) ----- */
+/* MvfBuilder::new, src/builder.rs:101-107 */
+MVF_API int mvf_builder_new(mvf_builder** out);
+MVF_API void mvf_builder_free(mvf_builder* b);
+/* MvfBuilder::add_vector_space, src/builder.rs:112-135 */
+MVF_API int mvf_builder_add_vector_space(mvf_builder* b, const char* name, uint32_t dimension,
+                                         int vector_type, int distance_metric, int data_type,
+                                         size_t* out_index);
+/* MvfBuilder::add_vectors, src/builder.rs:151-196: rows of f32, stored as the space's dtype
+ * (Float32 verbatim, Float16 round-to-nearest-even).  Int8/UInt8 -> MVF_ERR_BUILD like :192. */
+MVF_API int mvf_builder_add_vectors_f32(mvf_builder* b, const char* space, const float* rows,
+                                        size_t nrows, uint32_t dimension);
+/* extension the reference lacks: append rows already encoded in the space's dtype (the only way
+ * to write Int8/UInt8) */
+MVF_API int mvf_builder_add_vectors_raw(mvf_builder* b, const char* space, const void* rows,
+                                        size_t nrows, uint32_t dimension);
+/* MvfBuilder::add_metadata_column, src/builder.rs:211-236 (opaque bytes) */
+MVF_API int mvf_builder_add_metadata_column(mvf_builder* b, const char* name, int data_type,
+                                            const void* bytes, size_t nbytes);
+/* MvfBuilder::build + BuiltMvf::save, src/builder.rs:241-308,404-411, src/io.rs:41-46.
+ * Writes the correct total_vectors for every dtype (the reference halves it for Float16,
+ * src/builder.rs:476). */
+MVF_API int mvf_builder_save(mvf_builder* b, const char* path);
+
+/* ---------------------------------------------------------------- GPU engine (new) ------- */
+/* one engine per process, bound to one device.  Fails with MVF_ERR_CUDA when no sm_100 GPU. */
+MVF_API int mvf_gpu_init(int device, mvf_gpu** out);
+MVF_API void mvf_gpu_shutdown(mvf_gpu* g);
+/* run every search of this engine on the caller's CUDA stream (cudaStream_t as void*) */
+MVF_API int mvf_gpu_set_stream(mvf_gpu* g, void* cuda_stream);
+MVF_API int mvf_gpu_device_info(const mvf_gpu* g, int* sm_count, int* cc_major, int* cc_minor,
+                                uint64_t* free_bytes, uint64_t* total_bytes);
+/* multi-GPU: one process per GPU; rank 0 makes the id, the launcher broadcasts the 128 bytes */
+MVF_API int mvf_gpu_comm_unique_id(void* out_128_bytes);
+MVF_API int mvf_gpu_comm_init(mvf_gpu* g, const void* unique_id_128_bytes, int rank, int world);
+/* contiguous row shard of rank `rank`: [begin, begin+count) with ceil(n/world) rows per rank */
+MVF_API int mvf_shard_range(uint64_t n, int world, int rank, uint64_t* begin, uint64_t* count);
+
+/* residency: upload this rank's shard of the space once (page-locked registration of the mapped
+ * block, chunked async H2D, row norms computed on device).  Replaces the per-row
+ * get_vector()+as_f32() of examples/similarity_search.rs:147-149. */
+MVF_API int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* s, mvf_gpu_space** out);
+/* same from caller memory: `rows` holds local_n rows of the shard starting at global row
+ * row_base of a space with global_n rows */
+MVF_API int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type, int metric,
+                                    uint64_t local_n, uint32_t dimension, uint64_t row_base,
+                                    uint64_t global_n, mvf_gpu_space** out);
+/* bench/test only: fill this rank's shard of a global_n x dimension space on the device from the
+ * counter-based generator (DESIGN.md "synthetic data") */
+MVF_API int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t global_n,
+                                    uint32_t dimension, uint64_t seed, mvf_gpu_space** out);
+MVF_API void mvf_gpu_space_free(mvf_gpu_space* s);
+MVF_API int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base,
+                               uint64_t* global_n, uint32_t* dimension, int* data_type, int* metric);
+/* how the rows got to HBM: path 1 = cudaHostRegister'd mapping, 2 = pinned staging, 0 = generated */
+MVF_API int mvf_gpu_space_upload_stats(const mvf_gpu_space* s, int* path, double* seconds, uint64_t* bytes);
+/* copy rows / norms back (tests: device bytes == mapped bytes) */
+MVF_API int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out);
+MVF_API int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out_sq);
+
+/* find_top_k_similar(space, query, k), examples/similarity_search.rs:140-176, for nq queries at
+ * once.  queries: nq x dimension, HOST memory, dtype query_dtype (MVF_FLOAT32, or the space's own
+ * dtype; integer spaces take only their own dtype).  metric: MVF_METRIC_SPACE_DEFAULT or an
+ * override.  Outputs (HOST, caller-owned, nq*k each, best first; unused tail slots get id
+ * UINT64_MAX): out_ids = ScoredVector.index; out_scores = ScoredVector.score (L2 distance for
+ * float spaces, squared distance for integer spaces, dot for InnerProduct, 1-cos for Cosine);
+ * out_iscores (may be NULL) = exact int32 score for integer spaces with L2/InnerProduct.
+ * With a communicator every rank must call it with the same queries; every rank gets the result. */
+MVF_API int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq,
+                           uint32_t k, int metric, uint64_t* out_ids, float* out_scores,
+                           int32_t* out_iscores);
+/* same with DEVICE pointers, asynchronous on the engine stream (no host sync) */
+MVF_API int mvf_gpu_search_device(mvf_gpu_space* s, const void* d_queries, int query_dtype,
+                                  uint32_t nq, uint32_t k, int metric, uint64_t* d_out_ids,
+                                  float* d_out_scores, int32_t* d_out_iscores);
+/* path selection: 0 auto, 1 bandwidth scan (K1), 2 tensor-core contraction (K2) */
+MVF_API int mvf_gpu_set_path(mvf_gpu* g, int path);
+/* instrumentation: when enabled, searches bracket the dominant kernel with CUDA events on the
+ * engine stream; stats are cumulative since the last reset */
+MVF_API int mvf_gpu_profile(mvf_gpu* g, int enable);
+MVF_API int mvf_gpu_profile_read(mvf_gpu* g, double* scan_ms_total, uint64_t* scan_launches,
+                                 uint64_t* all_launches, int* last_path);
+MVF_API int mvf_gpu_synchronize(mvf_gpu* g);
+
+/* host helpers shared by callers that move candidates themselves (and by the tests) */
+MVF_API uint32_t mvf_ordered_key_f32(float v);
+MVF_API float mvf_ordered_key_to_f32(uint32_t key);
+/* product-side synthetic generator, host flavour (same definition as the device fill) */
+MVF_API int mvf_synth_fill_host(void* out, int data_type, uint64_t seed, uint64_t row0,
+                                uint64_t nrows, uint32_t dimension);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVF_B200_H */

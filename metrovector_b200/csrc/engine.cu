@@ -1,0 +1,697 @@
+// engine.cu -- the GPU engine behind the C ABI: residency (mmap -> HBM once per space, with row
+// norms), kernel dispatch for find_top_k_similar (examples/similarity_search.rs:140-176 of the
+// reference), and the row-sharded multi-GPU merge (one ncclAllGather of nq*k 64-bit candidates).
+// One engine = one process on one B200.  There is no CPU compute fallback: without a device every
+// entry point fails with MVF_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "c_api_common.hpp"
+#include "kernels.cuh"
+#include "tc_path.cuh"
+
+using namespace mvf;
+using mvf::k::u64;
+
+#define CUDA_CHECK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            throw MvfError::cuda(std::string(cudaGetErrorName(_e)) + ": " + cudaGetErrorString(_e) + " at " #expr); \
+    } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency; inside a torch process this resolves to the
+// libnccl.so.2 torch already loaded ------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    if (!api.handle) {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+        if (!api.handle) throw MvfError::nccl(std::string("cannot load libnccl: ") + dlerror());
+        api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+        api.CommDestroy = (int (*)(NcclComm))dlsym(api.handle, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy)
+            throw MvfError::nccl("libnccl is missing required symbols");
+    }
+    return api;
+}
+void nccl_check(int rc, const char* what) {
+    if (rc != 0) {
+        const char* s = nccl().GetErrorString ? nccl().GetErrorString(rc) : "?";
+        throw MvfError::nccl(std::string(what) + ": " + s);
+    }
+}
+constexpr int kNcclUint64 = 5;   // ncclUint64, nccl.h
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CUDA_CHECK(cudaMalloc(&p, n));
+        cap = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+uint32_t pow2ceil(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+}  // namespace
+
+struct mvf_gpu {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    NcclComm comm = nullptr;
+    int rank = 0, world = 1;
+    int path = 0;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    double scan_ms_total = 0.0;
+    uint64_t scan_launches = 0, all_launches = 0;
+    int last_path = 0;
+    int ctas_per_sm_cap = 0;   // MVF_SCAN_CTAS_PER_SM, 0 = occupancy
+    DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores;
+    std::map<std::pair<const void*, size_t>, int> occ_cache;
+    mvf::tc::TcState tc;
+};
+
+struct mvf_gpu_space {
+    mvf_gpu* g = nullptr;
+    int dtype = 0, metric = 0;
+    uint64_t local_n = 0, row_base = 0, global_n = 0;
+    uint32_t d = 0, pitch = 0;
+    unsigned char* rows = nullptr;
+    float* norm = nullptr;
+    float* sq = nullptr;
+    int upload_path = 0;       // 0 none/synthetic, 1 cudaHostRegister'd mapping, 2 pinned staging
+    double upload_seconds = 0.0;
+};
+
+namespace {
+
+void flush_profile(mvf_gpu* g) {
+    for (size_t i = 0; i < g->ev_used; i++) {
+        float ms = 0.f;
+        cudaEventSynchronize(g->ev_pool[i].second);
+        if (cudaEventElapsedTime(&ms, g->ev_pool[i].first, g->ev_pool[i].second) == cudaSuccess) g->scan_ms_total += ms;
+    }
+    g->ev_used = 0;
+}
+struct ScanTimer {   // brackets the dominant kernel with events when profiling is on
+    mvf_gpu* g; bool on = false; size_t idx = 0;
+    explicit ScanTimer(mvf_gpu* gg) : g(gg) {
+        if (!g->profile) return;
+        if (g->ev_used == g->ev_pool.size()) {
+            if (g->ev_pool.size() >= 8192) flush_profile(g);
+            if (g->ev_used == g->ev_pool.size()) {
+                cudaEvent_t a, b; CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+                g->ev_pool.push_back({a, b});
+            }
+        }
+        idx = g->ev_used++; on = true;
+        cudaEventRecord(g->ev_pool[idx].first, g->stream);
+    }
+    ~ScanTimer() { if (on) cudaEventRecord(g->ev_pool[idx].second, g->stream); }
+};
+
+int occupancy(mvf_gpu* g, const void* fn, int threads, size_t smem) {
+    auto key = std::make_pair(fn, smem);
+    auto it = g->occ_cache.find(key);
+    if (it != g->occ_cache.end()) return it->second;
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem));
+    if (nb < 1) throw MvfError::cuda("kernel does not fit on an SM (shared memory " + std::to_string(smem) + " B)");
+    g->occ_cache[key] = nb;
+    return nb;
+}
+
+// ---- K1 dispatch ------------------------------------------------------------------------------
+template <int DT> constexpr bool dt_is_float() { return DT == k::DT_F32 || DT == k::DT_F16; }
+
+struct ScanShape { bool wide; int LPR; uint32_t dpad; };
+template <int DT> ScanShape scan_shape(uint32_t pitch) {
+    const uint32_t C = pitch >> 4;
+    ScanShape s;
+    if (C > 16) { s.wide = true; s.LPR = 32; s.dpad = ((C + 31) / 32) * 32 * k::Traits<DT>::EPC; }
+    else { s.wide = false; s.LPR = (int)pow2ceil(C); s.dpad = (uint32_t)s.LPR * k::Traits<DT>::EPC; }
+    return s;
+}
+template <int DT> size_t scan_smem(int NQ, uint32_t P, uint32_t dpad) {
+    size_t q_bytes = (size_t)NQ * dpad * (dt_is_float<DT>() ? 4 : 1);
+    return (size_t)NQ * P * 8 + ((q_bytes + 15) & ~(size_t)15) + (size_t)NQ * sizeof(k::QueryConst) + 64;
+}
+
+template <int DT, int OP, int NQ, int R>
+void launch_scan_t(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, uint32_t* grid_out) {
+    const ScanShape sh = scan_shape<DT>(s->pitch);
+    const size_t smem = scan_smem<DT>(NQ, p.P, sh.dpad);
+    const void* fn = sh.wide ? (const void*)k::scan_topk_wide<DT, OP, NQ, R> : (const void*)k::scan_topk_narrow<DT, OP, NQ, R>;
+    int nb = occupancy(g, fn, k::kScanThreads, smem);
+    if (g->ctas_per_sm_cap > 0) nb = std::min(nb, g->ctas_per_sm_cap);
+    const uint64_t rows_per_group = sh.wide ? (uint64_t)R : (uint64_t)R * (32 / sh.LPR);
+    const uint64_t groups = (s->local_n + rows_per_group - 1) / rows_per_group;
+    uint64_t want = (groups + k::kScanWarps - 1) / k::kScanWarps;
+    uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb, want));
+    // the candidate buffer was sized by the caller with scan_grid_bound(); keep within it
+    *grid_out = grid;
+    ScanTimer t(g);
+    if (sh.wide) k::scan_topk_wide<DT, OP, NQ, R><<<grid, k::kScanThreads, smem, g->stream>>>(p);
+    else k::scan_topk_narrow<DT, OP, NQ, R><<<grid, k::kScanThreads, smem, g->stream>>>(p, sh.LPR);
+    CUDA_CHECK(cudaGetLastError());
+    g->scan_launches++; g->all_launches++;
+}
+
+template <int DT, int OP>
+void launch_scan_nq(mvf_gpu* g, const mvf_gpu_space* s, const k::ScanParams& p, int NQ, uint32_t* grid_out) {
+    switch (NQ) {
+        case 1: launch_scan_t<DT, OP, 1, 8>(g, s, p, grid_out); break;
+        case 2: launch_scan_t<DT, OP, 2, 8>(g, s, p, grid_out); break;
+        case 4: launch_scan_t<DT, OP, 4, 4>(g, s, p, grid_out); break;
+        default: launch_scan_t<DT, OP, 8, 2>(g, s, p, grid_out); break;
+    }
+}
+template <int DT>
+void launch_scan_dt(mvf_gpu* g, const mvf_gpu_space* s, const k::ScanParams& p, int NQ, uint32_t* grid_out) {
+    if (p.metric == k::M_L2) launch_scan_nq<DT, k::OP_L2>(g, s, p, NQ, grid_out);
+    else launch_scan_nq<DT, k::OP_DOT>(g, s, p, NQ, grid_out);
+}
+void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, const k::ScanParams& p, int NQ, uint32_t* grid_out) {
+    switch (s->dtype) {
+        case k::DT_F32: launch_scan_dt<k::DT_F32>(g, s, p, NQ, grid_out); break;
+        case k::DT_F16: launch_scan_dt<k::DT_F16>(g, s, p, NQ, grid_out); break;
+        case k::DT_I8: launch_scan_dt<k::DT_I8>(g, s, p, NQ, grid_out); break;
+        default: launch_scan_dt<k::DT_U8>(g, s, p, NQ, grid_out); break;
+    }
+}
+size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
+    switch (dtype) {
+        case k::DT_F32: return scan_smem<k::DT_F32>(NQ, P, scan_shape<k::DT_F32>(pitch).dpad);
+        case k::DT_F16: return scan_smem<k::DT_F16>(NQ, P, scan_shape<k::DT_F16>(pitch).dpad);
+        case k::DT_I8: return scan_smem<k::DT_I8>(NQ, P, scan_shape<k::DT_I8>(pitch).dpad);
+        default: return scan_smem<k::DT_U8>(NQ, P, scan_shape<k::DT_U8>(pitch).dpad);
+    }
+}
+
+void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
+    const uint64_t total = (uint64_t)mp.nlists * mp.k + mp.k;
+    uint32_t P = pow2ceil((uint32_t)std::min<uint64_t>(total, 16384));
+    P = std::max<uint32_t>(P, std::max<uint32_t>(64, 2 * pow2ceil(mp.k)));
+    P = std::min<uint32_t>(P, 16384);
+    mp.P = P;
+    const size_t smem = (size_t)P * 8;
+    if (smem > 48 * 1024) {
+        static bool set = false;
+        if (!set) { CUDA_CHECK(cudaFuncSetAttribute(k::merge_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8)); set = true; }
+    }
+    const int threads = (int)std::min<uint32_t>(1024, std::max<uint32_t>(32, P / 2));
+    k::merge_topk<<<nq, threads, smem, g->stream>>>(mp);
+    CUDA_CHECK(cudaGetLastError());
+    g->all_launches++;
+}
+
+void validate_query(const mvf_gpu_space* s, int qdtype, uint32_t nq, uint32_t k, int metric) {
+    if (nq == 0) throw MvfError::build_error("search needs at least one query");
+    if (k == 0 || k > 1024) throw MvfError::build_error("k must be in 1..1024");
+    if (metric < 0 || metric > 2) throw MvfError::build_error("unsupported distance metric (L2, InnerProduct, Cosine)");
+    const bool fspace = s->dtype == k::DT_F32 || s->dtype == k::DT_F16;
+    if (fspace) {
+        if (!(qdtype == k::DT_F32 || (qdtype == k::DT_F16 && s->dtype == k::DT_F16)))
+            throw MvfError::build_error("float spaces take Float32 queries (Float16 spaces also Float16)");
+    } else if (qdtype != s->dtype) {
+        throw MvfError::build_error("integer spaces take queries in their own data type");
+    }
+}
+
+// Full search with device-resident queries/outputs; asynchronous on g->stream.
+void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t nq, uint32_t kk, int metric,
+                   uint64_t* d_ids, float* d_scores, int32_t* d_iscores) {
+    mvf_gpu* g = s->g;
+    if (metric == MVF_METRIC_SPACE_DEFAULT) metric = s->metric;
+    validate_query(s, qdtype, nq, kk, metric);
+    CUDA_CHECK(cudaSetDevice(g->device));
+    const bool multi = g->world > 1 && g->comm;
+    u64* packed_local = nullptr;
+    if (multi) { g->packed_local.reserve((size_t)nq * kk * 8); packed_local = (u64*)g->packed_local.p; }
+
+    bool done = false;
+    if (mvf::tc::eligible(g->tc, g->path, s->dtype, qdtype, metric, nq, kk, s->local_n, s->d, s->pitch)) {
+        mvf::tc::SearchArgs a;
+        a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
+        a.dtype = s->dtype; a.metric = metric; a.queries = d_queries; a.nq = nq; a.k = kk;
+        a.id_add = (uint32_t)s->row_base;
+        a.out_packed = packed_local; a.out_ids = multi ? nullptr : d_ids; a.out_scores = multi ? nullptr : d_scores;
+        a.out_iscores = multi ? nullptr : d_iscores;
+        ScanTimer t(g);
+        uint64_t launches = 0;
+        mvf::tc::search(g->tc, a, g->stream, g->sm_count, &launches);
+        g->scan_launches++; g->all_launches += launches;
+        g->last_path = 2;
+        done = true;
+    }
+    if (!done) {
+        g->last_path = 1;
+        const uint32_t P = std::max<uint32_t>(8, pow2ceil(k::kScanWarps * kk));
+        // widest query group whose lists + staged queries fit comfortably in shared memory
+        int NQmax = 8;
+        while (NQmax > 1 && scan_smem_any(s->dtype, NQmax, P, s->pitch) > 96 * 1024) NQmax >>= 1;
+        if (scan_smem_any(s->dtype, 1, P, s->pitch) > g->smem_optin)
+            throw MvfError::build_error("dimension * k too large for the scan kernel's shared memory");
+        const size_t grid_bound = (size_t)g->sm_count * 32;
+        g->cand.reserve((size_t)NQmax * grid_bound * kk * 8);
+        uint32_t q0 = 0;
+        while (q0 < nq) {
+            int NQ = NQmax;
+            while ((uint32_t)NQ > nq - q0) NQ >>= 1;
+            k::ScanParams p;
+            p.rows = s->rows; p.norm = s->norm; p.queries = d_queries; p.cand = (u64*)g->cand.p;
+            p.n = s->local_n; p.d = s->d; p.pitch = s->pitch; p.k = kk; p.P = P; p.metric = metric; p.qdtype = qdtype; p.q0 = q0;
+            uint32_t grid = 0;
+            if (s->local_n > 0) launch_scan(g, s, p, NQ, &grid);
+            k::MergeParams mp;
+            mp.in = (const u64*)g->cand.p; mp.q_stride = (size_t)grid * kk; mp.list_stride = kk; mp.nlists = grid; mp.k = kk;
+            mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype;
+            const size_t o = (size_t)q0 * kk;
+            mp.out_packed = multi ? packed_local + o : nullptr;
+            mp.out_ids = multi ? nullptr : d_ids + o;
+            mp.out_scores = multi ? nullptr : (d_scores ? d_scores + o : nullptr);
+            mp.out_iscores = multi ? nullptr : (d_iscores ? d_iscores + o : nullptr);
+            launch_merge(g, mp, (uint32_t)NQ);
+            q0 += (uint32_t)NQ;
+        }
+    }
+    if (multi) {
+        // one exchange step: every rank contributes its nq*k best (global ids already applied)
+        const size_t cnt = (size_t)nq * kk;
+        g->gathered.reserve(cnt * 8 * (size_t)g->world);
+        nccl_check(nccl().AllGather(packed_local, g->gathered.p, cnt, kNcclUint64, g->comm, g->stream), "ncclAllGather");
+        g->all_launches++;
+        k::MergeParams mp;
+        mp.in = (const u64*)g->gathered.p; mp.q_stride = kk; mp.list_stride = cnt; mp.nlists = (uint32_t)g->world; mp.k = kk;
+        mp.id_add = 0; mp.metric = metric; mp.dtype = s->dtype;
+        mp.out_packed = nullptr; mp.out_ids = d_ids; mp.out_scores = d_scores; mp.out_iscores = d_iscores;
+        launch_merge(g, mp, nq);
+    }
+}
+
+// ---- residency ----------------------------------------------------------------------------------
+mvf_gpu_space* alloc_space(mvf_gpu* g, int dtype, int metric, uint64_t local_n, uint32_t d, uint64_t row_base,
+                           uint64_t global_n) {
+    if (dtype < 0 || dtype > 3) throw MvfError::build_error("Unsupported vector data type");
+    if (metric == 255) throw MvfError::build_error("Custom distance metrics are not searchable");
+    if (metric < 0 || metric > 2) throw MvfError::build_error("unsupported distance metric");
+    if (d == 0) throw MvfError::build_error("vector space has dimension 0");
+    if (global_n > 0xffffffffull || local_n >= 0xffffffffull)
+        throw MvfError::build_error("spaces with more than 2^32 rows are not supported by this build");
+    const size_t es = element_size((DataType)dtype);
+    if ((dtype == k::DT_I8 || dtype == k::DT_U8) && d > 33025)
+        throw MvfError::build_error("integer spaces support dimension <= 33025 (int32 accumulation)");
+    const uint64_t pitch64 = ((uint64_t)d * es + 15) & ~15ull;
+    if (pitch64 > (1u << 20)) throw MvfError::build_error("row too large (max 1 MiB)");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    mvf_gpu_space* s = new mvf_gpu_space();
+    s->g = g; s->dtype = dtype; s->metric = metric; s->local_n = local_n; s->row_base = row_base; s->global_n = global_n;
+    s->d = d; s->pitch = (uint32_t)pitch64;
+    try {
+        const size_t bytes = std::max<size_t>((size_t)local_n * s->pitch, 16);
+        CUDA_CHECK(cudaMalloc((void**)&s->rows, bytes));
+        CUDA_CHECK(cudaMalloc((void**)&s->norm, std::max<size_t>(local_n * 4, 16)));
+        CUDA_CHECK(cudaMalloc((void**)&s->sq, std::max<size_t>(local_n * 4, 16)));
+    } catch (...) {
+        cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); delete s; throw;
+    }
+    return s;
+}
+
+void compute_norms(mvf_gpu_space* s) {
+    if (s->local_n == 0) return;
+    mvf_gpu* g = s->g;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((s->local_n + 7) / 8, (uint64_t)g->sm_count * 8);
+    switch (s->dtype) {
+        case k::DT_F32: k::row_norms<k::DT_F32><<<grid, 256, 0, g->stream>>>(s->rows, s->local_n, s->pitch, s->norm, s->sq); break;
+        case k::DT_F16: k::row_norms<k::DT_F16><<<grid, 256, 0, g->stream>>>(s->rows, s->local_n, s->pitch, s->norm, s->sq); break;
+        case k::DT_I8: k::row_norms<k::DT_I8><<<grid, 256, 0, g->stream>>>(s->rows, s->local_n, s->pitch, s->norm, s->sq); break;
+        default: k::row_norms<k::DT_U8><<<grid, 256, 0, g->stream>>>(s->rows, s->local_n, s->pitch, s->norm, s->sq); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    g->all_launches++;
+}
+
+// Copy `nrows` rows of `rowbytes` from host memory (any alignment, possibly a read-only file
+// mapping) into the pitched device buffer.  First choice: page-lock the source range in place
+// (cudaHostRegister, read-only) and DMA straight out of the mapping; if the platform refuses,
+// stream through two pinned staging buffers.  Both are residency paths, not compute fallbacks.
+void upload_rows(mvf_gpu_space* s, const unsigned char* src, uint64_t nrows, size_t rowbytes, bool try_register) {
+    mvf_gpu* g = s->g;
+    if (nrows == 0) return;
+    auto t0 = std::chrono::steady_clock::now();
+    const size_t pitch = s->pitch;
+    if (pitch != rowbytes) CUDA_CHECK(cudaMemsetAsync(s->rows, 0, (size_t)nrows * pitch, g->stream));
+    auto copy_rows = [&](const unsigned char* from, uint64_t r0, uint64_t cnt) {
+        unsigned char* dst = s->rows + r0 * pitch;
+        if (pitch == rowbytes) CUDA_CHECK(cudaMemcpyAsync(dst, from, cnt * rowbytes, cudaMemcpyHostToDevice, g->stream));
+        else CUDA_CHECK(cudaMemcpy2DAsync(dst, pitch, from, rowbytes, rowbytes, cnt, cudaMemcpyHostToDevice, g->stream));
+    };
+    const uint64_t window_rows = std::max<uint64_t>(1, (1ull << 30) / rowbytes);
+    uint64_t r = 0;
+    bool registered_ok = try_register;
+    const long page = 4096;
+    while (registered_ok && r < nrows) {
+        uint64_t cnt = std::min<uint64_t>(window_rows, nrows - r);
+        const unsigned char* a = src + r * rowbytes;
+        uintptr_t lo = (uintptr_t)a & ~(uintptr_t)(page - 1);
+        uintptr_t hi = ((uintptr_t)a + cnt * rowbytes + page - 1) & ~(uintptr_t)(page - 1);
+        cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterReadOnly);
+        if (e != cudaSuccess) { cudaGetLastError(); registered_ok = false; break; }
+        try {
+            copy_rows(a, r, cnt);
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        } catch (...) { cudaHostUnregister((void*)lo); throw; }
+        cudaHostUnregister((void*)lo);
+        s->upload_path = 1;
+        r += cnt;
+    }
+    if (r < nrows) {
+        s->upload_path = 2;
+        const size_t stage_bytes = std::max<size_t>(32u << 20, rowbytes);
+        const uint64_t stage_rows = stage_bytes / rowbytes;
+        unsigned char* stage[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        try {
+            for (int i = 0; i < 2; i++) {
+                CUDA_CHECK(cudaMallocHost((void**)&stage[i], stage_rows * rowbytes));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            }
+            int b = 0;
+            while (r < nrows) {
+                uint64_t cnt = std::min<uint64_t>(stage_rows, nrows - r);
+                CUDA_CHECK(cudaEventSynchronize(ev[b]));
+                std::memcpy(stage[b], src + r * rowbytes, cnt * rowbytes);
+                copy_rows(stage[b], r, cnt);
+                CUDA_CHECK(cudaEventRecord(ev[b], g->stream));
+                r += cnt; b ^= 1;
+            }
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        } catch (...) {
+            cudaStreamSynchronize(g->stream);
+            for (int i = 0; i < 2; i++) { if (stage[i]) cudaFreeHost(stage[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+            throw;
+        }
+        for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); cudaEventDestroy(ev[i]); }
+    }
+    s->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void free_space(mvf_gpu_space* s) {
+    if (!s) return;
+    cudaSetDevice(s->g->device);
+    cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq);
+    delete s;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mvf_gpu_init(int device, mvf_gpu** out) {
+    return guard([&] {
+        *out = nullptr;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            throw MvfError::cuda("no CUDA device available (this library has no CPU fallback)");
+        }
+        if (device < 0 || device >= count) throw MvfError::cuda("invalid device ordinal " + std::to_string(device));
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw MvfError::cuda("device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                 "; this library carries sm_100a code only");
+        mvf_gpu* g = new mvf_gpu();
+        g->device = device; g->sm_count = prop.multiProcessorCount; g->cc_major = prop.major; g->cc_minor = prop.minor;
+        g->smem_optin = prop.sharedMemPerBlockOptin;
+        cudaError_t se = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete g; CUDA_CHECK(se); }
+        g->own_stream = true;
+        if (const char* c = std::getenv("MVF_SCAN_CTAS_PER_SM")) g->ctas_per_sm_cap = std::atoi(c);
+        *out = g;
+    });
+}
+
+void mvf_gpu_shutdown(mvf_gpu* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaStreamSynchronize(g->stream);
+    if (g->comm) { try { nccl().CommDestroy(g->comm); } catch (...) {} }
+    for (auto& e : g->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    g->cand.release(); g->packed_local.release(); g->gathered.release(); g->queries.release();
+    g->out_ids.release(); g->out_scores.release(); g->out_iscores.release();
+    mvf::tc::release(g->tc);
+    if (g->own_stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+int mvf_gpu_set_stream(mvf_gpu* g, void* cuda_stream) {
+    return guard([&] {
+        CUDA_CHECK(cudaSetDevice(g->device));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        if (g->own_stream) { cudaStreamDestroy(g->stream); g->own_stream = false; }
+        g->stream = (cudaStream_t)cuda_stream;
+    });
+}
+
+int mvf_gpu_device_info(const mvf_gpu* g, int* sm_count, int* cc_major, int* cc_minor, uint64_t* free_bytes,
+                        uint64_t* total_bytes) {
+    return guard([&] {
+        CUDA_CHECK(cudaSetDevice(g->device));
+        size_t f = 0, t = 0;
+        CUDA_CHECK(cudaMemGetInfo(&f, &t));
+        if (sm_count) *sm_count = g->sm_count;
+        if (cc_major) *cc_major = g->cc_major;
+        if (cc_minor) *cc_minor = g->cc_minor;
+        if (free_bytes) *free_bytes = f;
+        if (total_bytes) *total_bytes = t;
+    });
+}
+
+int mvf_gpu_comm_unique_id(void* out_128_bytes) {
+    return guard([&] {
+        NcclUniqueId id;
+        nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(out_128_bytes, &id, 128);
+    });
+}
+
+int mvf_gpu_comm_init(mvf_gpu* g, const void* unique_id_128_bytes, int rank, int world) {
+    return guard([&] {
+        if (world < 1 || rank < 0 || rank >= world) throw MvfError::nccl("invalid rank/world");
+        CUDA_CHECK(cudaSetDevice(g->device));
+        g->rank = rank; g->world = world;
+        if (world == 1) return;
+        NcclUniqueId id; std::memcpy(&id, unique_id_128_bytes, 128);
+        nccl_check(nccl().CommInitRank(&g->comm, world, id, rank), "ncclCommInitRank");
+    });
+}
+
+int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* sp, mvf_gpu_space** out) {
+    return guard([&] {
+        *out = nullptr;
+        const VectorSpace& vs = sp->vs;
+        if (vs.vector_type() != VectorType::Dense)
+            throw MvfError(ErrorKind::InvalidVectorType, "Invalid vector type: expected Dense, got Sparse");
+        const int dtype = (int)vs.data_type();
+        const size_t es = element_size(vs.data_type());
+        if (!es) throw MvfError::build_error("Unsupported vector data type");
+        // exactly the rows `for i in 0..total_vectors()` + get_vector can visit (similarity_search.rs:147-148)
+        const uint64_t n = vs.scannable_vectors();
+        uint64_t begin = 0, count = n;
+        shard_range(n, g->world, g->rank, &begin, &count);
+        mvf_gpu_space* s = alloc_space(g, dtype, (int)vs.distance_metric(), count, vs.dimension(), begin, n);
+        try {
+            if (count) {
+                // map_vector_range semantics (vector_space.rs:155-188) without the total_vectors cap
+                // (scannable_vectors already applied both limits)
+                size_t nbytes = 0;
+                const uint8_t* base = vs.map_vector_range(begin, count, &nbytes);
+                upload_rows(s, base, count, (size_t)vs.dimension() * es, !std::getenv("MVF_NO_HOST_REGISTER"));
+                compute_norms(s);
+                CUDA_CHECK(cudaStreamSynchronize(g->stream));
+            }
+        } catch (...) { free_space(s); throw; }
+        *out = s;
+    });
+}
+
+int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type, int metric, uint64_t local_n, uint32_t dimension,
+                            uint64_t row_base, uint64_t global_n, mvf_gpu_space** out) {
+    return guard([&] {
+        *out = nullptr;
+        if (row_base + local_n > global_n) throw MvfError::index_out_of_bounds(row_base + local_n, global_n);
+        mvf_gpu_space* s = alloc_space(g, data_type, metric, local_n, dimension, row_base, global_n);
+        try {
+            upload_rows(s, (const unsigned char*)rows, local_n, (size_t)dimension * element_size((DataType)data_type), false);
+            compute_norms(s);
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        } catch (...) { free_space(s); throw; }
+        *out = s;
+    });
+}
+
+int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t global_n, uint32_t dimension, uint64_t seed,
+                            mvf_gpu_space** out) {
+    return guard([&] {
+        *out = nullptr;
+        uint64_t begin = 0, count = global_n;
+        shard_range(global_n, g->world, g->rank, &begin, &count);
+        mvf_gpu_space* s = alloc_space(g, data_type, metric, count, dimension, begin, global_n);
+        try {
+            if (count) {
+                const uint64_t sk = synth::sm64(seed);
+                const uint32_t grid = (uint32_t)g->sm_count * 16;
+                switch (data_type) {
+                    case k::DT_F32: k::synth_fill<k::DT_F32><<<grid, 256, 0, g->stream>>>(s->rows, count, dimension, s->pitch, sk, begin); break;
+                    case k::DT_F16: k::synth_fill<k::DT_F16><<<grid, 256, 0, g->stream>>>(s->rows, count, dimension, s->pitch, sk, begin); break;
+                    case k::DT_I8: k::synth_fill<k::DT_I8><<<grid, 256, 0, g->stream>>>(s->rows, count, dimension, s->pitch, sk, begin); break;
+                    default: k::synth_fill<k::DT_U8><<<grid, 256, 0, g->stream>>>(s->rows, count, dimension, s->pitch, sk, begin); break;
+                }
+                CUDA_CHECK(cudaGetLastError());
+                g->all_launches++;
+                compute_norms(s);
+                CUDA_CHECK(cudaStreamSynchronize(g->stream));
+            }
+        } catch (...) { free_space(s); throw; }
+        *out = s;
+    });
+}
+
+void mvf_gpu_space_free(mvf_gpu_space* s) { free_space(s); }
+
+int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base, uint64_t* global_n,
+                       uint32_t* dimension, int* data_type, int* metric) {
+    return guard([&] {
+        if (local_n) *local_n = s->local_n;
+        if (row_base) *row_base = s->row_base;
+        if (global_n) *global_n = s->global_n;
+        if (dimension) *dimension = s->d;
+        if (data_type) *data_type = s->dtype;
+        if (metric) *metric = s->metric;
+    });
+}
+
+int mvf_gpu_space_upload_stats(const mvf_gpu_space* s, int* path, double* seconds, uint64_t* bytes) {
+    return guard([&] {
+        if (path) *path = s->upload_path;
+        if (seconds) *seconds = s->upload_seconds;
+        if (bytes) *bytes = s->local_n * (uint64_t)s->d * element_size((DataType)s->dtype);
+    });
+}
+
+int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out) {
+    return guard([&] {
+        if (local_start + count > s->local_n) throw MvfError::index_out_of_bounds(local_start + count, s->local_n);
+        if (!count) return;
+        CUDA_CHECK(cudaSetDevice(s->g->device));
+        const size_t rowbytes = (size_t)s->d * element_size((DataType)s->dtype);
+        CUDA_CHECK(cudaStreamSynchronize(s->g->stream));
+        CUDA_CHECK(cudaMemcpy2D(out, rowbytes, s->rows + local_start * s->pitch, s->pitch, rowbytes, count, cudaMemcpyDeviceToHost));
+    });
+}
+
+int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out_sq) {
+    return guard([&] {
+        CUDA_CHECK(cudaSetDevice(s->g->device));
+        CUDA_CHECK(cudaStreamSynchronize(s->g->stream));
+        if (out_norm) CUDA_CHECK(cudaMemcpy(out_norm, s->norm, s->local_n * 4, cudaMemcpyDeviceToHost));
+        if (out_sq) CUDA_CHECK(cudaMemcpy(out_sq, s->sq, s->local_n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int mvf_gpu_search_device(mvf_gpu_space* s, const void* d_queries, int query_dtype, uint32_t nq, uint32_t k, int metric,
+                          uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_iscores) {
+    return guard([&] { search_device(s, d_queries, query_dtype, nq, k, metric, d_out_ids, d_out_scores, d_out_iscores); });
+}
+
+int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq, uint32_t k, int metric,
+                   uint64_t* out_ids, float* out_scores, int32_t* out_iscores) {
+    return guard([&] {
+        mvf_gpu* g = s->g;
+        if (!queries || !out_ids) throw MvfError::build_error("null argument");
+        if (nq == 0) throw MvfError::build_error("search needs at least one query");
+        if (query_dtype < 0 || query_dtype > 3) throw MvfError::build_error("unsupported query data type");
+        CUDA_CHECK(cudaSetDevice(g->device));
+        const size_t qbytes = (size_t)nq * s->d * element_size((DataType)query_dtype);
+        const size_t cnt = (size_t)nq * k;
+        g->queries.reserve(std::max<size_t>(qbytes, 16));
+        g->out_ids.reserve(cnt * 8); g->out_scores.reserve(cnt * 4); g->out_iscores.reserve(cnt * 4);
+        CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
+        search_device(s, g->queries.p, query_dtype, nq, k, metric, (uint64_t*)g->out_ids.p, (float*)g->out_scores.p,
+                      out_iscores ? (int32_t*)g->out_iscores.p : nullptr);
+        CUDA_CHECK(cudaMemcpyAsync(out_ids, g->out_ids.p, cnt * 8, cudaMemcpyDeviceToHost, g->stream));
+        if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, g->out_scores.p, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
+        if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, g->out_iscores.p, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    });
+}
+
+int mvf_gpu_set_path(mvf_gpu* g, int path) {
+    return guard([&] {
+        if (path < 0 || path > 2) throw MvfError::build_error("path must be 0 (auto), 1 (scan) or 2 (tensor)");
+        g->path = path;
+    });
+}
+
+int mvf_gpu_profile(mvf_gpu* g, int enable) {
+    return guard([&] {
+        CUDA_CHECK(cudaSetDevice(g->device));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        flush_profile(g);
+        g->profile = enable != 0;
+        g->scan_ms_total = 0.0; g->scan_launches = 0; g->all_launches = 0;
+    });
+}
+
+int mvf_gpu_profile_read(mvf_gpu* g, double* scan_ms_total, uint64_t* scan_launches, uint64_t* all_launches, int* last_path) {
+    return guard([&] {
+        CUDA_CHECK(cudaSetDevice(g->device));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        flush_profile(g);
+        if (scan_ms_total) *scan_ms_total = g->scan_ms_total;
+        if (scan_launches) *scan_launches = g->scan_launches;
+        if (all_launches) *all_launches = g->all_launches;
+        if (last_path) *last_path = g->last_path;
+    });
+}
+
+int mvf_gpu_synchronize(mvf_gpu* g) {
+    return guard([&] { CUDA_CHECK(cudaSetDevice(g->device)); CUDA_CHECK(cudaStreamSynchronize(g->stream)); });
+}
+
+}  // extern "C"
