@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- brute-force top-k QPS of the B200 scan, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload B] [--impl ours|reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N>1).  A "step" is one search of
+one query batch over the whole (row-sharded) database: kernels + merge (+ one NCCL allgather and
+the global merge when N>1).  Rank 0 prints ONE JSON line.
+
+  value  QPS with the query batch already resident in HBM, timed with CUDA events on the engine's
+         stream, max over ranks.
+  e2e    QPS through the public call a user makes (mvf_gpu_search with HOST buffers): per step the
+         H2D copy of the queries from pinned memory, the search, the D2H copy of ids+scores, and
+         the stream sync are all inside the timed region.
+  roofline  the scan kernel alone (CUDA events around it, on its stream) against the measured
+         HBM peak in MEASURED_PEAKS.json; algorithmic bytes = local_rows * dimension * elem_size
+         per query batch.
+  cpu_baseline  the CPU oracle (a port of the reference's scan; the reference is Rust and cannot be
+         built in this image) timed on this box's cores on a bounded row sample, scaled to N rows.
+
+Workloads are BASELINE.json's configs; the database is synthetic (counter-based generator, filled
+on the device), row-sharded over the ranks ("strong" scaling: the global database is fixed).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name: (rows, dim, dtype, metric, k, batch)      dtype/metric codes = schema/types.fbs
+WORKLOADS = {
+    "A": (100_000, 128, 0, 2, 10, 1),            # examples/similarity_search-sized: 100k x 128 f32 cosine
+    "B": (1_000_000, 768, 0, 0, 10, 1),          # 1M x 768 f32 L2 top-10, batch 1 (HBM-bound scan)
+    "C": (10_000_000, 768, 1, 2, 100, 4096),     # 10M x 768 f16 cosine top-100, batch 4096 (tensor path)
+    "D": (100_000_000, 768, 1, 2, 10, 1),        # 100M x 768 f16 cosine top-10, batch 1
+    "D1024": (100_000_000, 768, 1, 2, 10, 1024),
+    "E": (1_000_000_000, 128, 3, 0, 10, 1),      # 1B x 128 u8 L2 top-10 (SIFT1B-shaped)
+    "E1024": (1_000_000_000, 128, 3, 0, 10, 1024),
+}
+DT_NAME = {0: "f32", 1: "f16", 2: "i8", 3: "u8"}
+ARITH = {0: "f32", 1: "f32", 2: "int32", 3: "int32"}
+METRIC_NAME = {0: "L2", 1: "InnerProduct", 2: "Cosine"}
+ES = {0: 4, 1: 2, 2: 1, 3: 1}
+DB_SEED, Q_SEED = 0x4D564631, 0x4D564632
+
+
+def describe(wl, n, d, dt, metric, k, batch):
+    return "%s: %dx%d %s %s top-%d batch %d" % (wl, n, d, DT_NAME[dt], METRIC_NAME[metric], k, batch)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the measurement loops run."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while not self.stop_flag and self.ok:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_scan_qps(n, d, dt, metric, k, budget_rows):
+    """Oracle scan on a bounded sample of the same workload, all host threads; QPS scaled to n rows."""
+    import oracle
+    threads = os.cpu_count() or 1
+    sample = int(min(n, budget_rows))
+    db = oracle.synth(dt, DB_SEED, 0, sample, d, threads=threads)
+    q = oracle.synth(dt, Q_SEED, 0, 2, d)
+    if dt in (0, 1):
+        q = q.astype(np.float32)
+    oracle.scan_timed(db, dt, metric, q[:1], k, threads)            # warm the pages
+    sec, _, _ = oracle.scan_timed(db, dt, metric, q, k, threads)
+    per_query_sample = sec / q.shape[0]
+    qps = 1.0 / (per_query_sample * (n / sample))
+    return qps, threads, sample, per_query_sample
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's scan on the host CPU (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    n, d, dt, metric, k, batch = WORKLOADS[args.workload]
+    import oracle
+    threads = os.cpu_count() or 1
+    # bounded sample: ~0.4 GB of rows per step keeps W+K steps within minutes
+    sample = int(min(n, max(4096, (400 << 20) // (d * ES[dt]))))
+    db = oracle.synth(dt, DB_SEED, 0, sample, d, threads=threads)
+    qs = oracle.synth(dt, Q_SEED, 0, args.warmup + args.steps, d)
+    if dt in (0, 1):
+        qs = qs.astype(np.float32)
+    for i in range(args.warmup):
+        oracle.scan_timed(db, dt, metric, qs[i:i + 1], k, threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        oracle.scan_timed(db, dt, metric, qs[args.warmup + i:args.warmup + i + 1], k, threads)
+    sec = time.perf_counter() - t0
+    per_step_full = (sec / args.steps) * (n / sample) * batch      # one step = one batch over all n rows
+    qps = batch / per_step_full
+    line = {
+        "impl": "reference", "metric": "brute-force top-k QPS", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_full * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": ARITH[dt], "data": "synthetic",
+        "config": {"workload": describe(args.workload, n, d, dt, metric, k, batch)},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d rows per step, time scaled linearly to all rows" % (sample, n)},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MVF_BENCH_WORKLOAD", "B"), choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the row count (debug)")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 scan kernel, 2 tensor-core kernel")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import metrovector_b200 as mv
+
+    n, d, dt, metric, k, batch = WORKLOADS[args.workload]
+    if args.rows:
+        n = args.rows
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    stream = torch.cuda.Stream()
+    eng = mv.GpuEngine(local_rank)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_path(args.path)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(mv.GpuEngine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    gs = eng.synthetic(dt, metric, n, d, DB_SEED)             # this rank's shard, generated in HBM
+    es = ES[dt]
+    qnp = np.float32 if dt in (0, 1) else (np.int8 if dt == 2 else np.uint8)
+    qdt = 0 if dt in (0, 1) else dt
+    if dt == 1 and batch >= 256:
+        qnp, qdt = np.float16, 1                              # the tensor path takes queries in the space's dtype
+    nbatches = args.warmup + args.steps
+    distinct = min(nbatches, max(1, (256 << 20) // max(1, batch * d * np.dtype(qnp).itemsize)))
+    host_q = mv.synth_fill_host(dt, Q_SEED, 0, distinct * batch, d)
+    if qnp == np.float32 and dt == 1:
+        host_q = host_q.astype(np.float32)
+    q_pinned = torch.from_numpy(np.ascontiguousarray(host_q.reshape(distinct, batch * d))).pin_memory()
+    q_dev = q_pinned.cuda()
+    qbytes = batch * d * np.dtype(qnp).itemsize
+    ids_dev = torch.empty((batch, k), dtype=torch.int64, device="cuda")
+    sc_dev = torch.empty((batch, k), dtype=torch.float32, device="cuda")
+    ids_host = torch.empty((batch, k), dtype=torch.int64).pin_memory()
+    sc_host = torch.empty((batch, k), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        j = i % distinct
+        gs.search_device(q_dev.data_ptr() + j * qbytes, qdt, batch, k, metric, ids_dev.data_ptr(), sc_dev.data_ptr())
+
+    def step_host(i):
+        j = i % distinct
+        gs.search_raw(q_pinned.data_ptr() + j * qbytes, qdt, batch, k, metric, ids_host.data_ptr(), sc_host.data_ptr())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    with torch.cuda.stream(stream):
+        # ---- device-resident throughput -----------------------------------------------------
+        for i in range(args.warmup):
+            step_device(i)
+        barrier()
+        eng.profile(False)                                     # resets the launch counters
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(args.steps):
+            step_device(args.warmup + i)
+        ev1.record(stream)
+        barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+        launches = eng.profile_read()["all_launches"]
+        # ---- end to end through the host-buffer call ----------------------------------------
+        for i in range(args.warmup):
+            step_host(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_host(args.warmup + i)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        # ---- the scan kernel alone (roofline) -----------------------------------------------
+        eng.profile(True)
+        for i in range(args.steps):
+            step_device(args.warmup + i)
+        prof = eng.profile_read()
+        eng.profile(False)
+    sampler.stop_flag = True
+    sampler.join()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # sanity of the last device result on rank 0: recompute the k returned rows' scores on the host
+    verified = None
+    if rank == 0:
+        try:
+            import oracle
+            ids = ids_dev.cpu().numpy().astype(np.uint64)[0]
+            sc = sc_dev.cpu().numpy()[0]
+            j = (args.warmup + args.steps - 1) % distinct
+            q0 = host_q.reshape(distinct, batch, d)[j, 0]
+            ok = True
+            for gid, s in zip(ids[:k], sc[:k]):
+                row = mv.synth_fill_host(dt, DB_SEED, int(gid), 1, d)[0]
+                ref, iref, _ = oracle.score_row(row, dt, metric, q0.astype(np.float32) if dt in (0, 1) else q0)
+                ok = ok and (abs(ref - s) <= 1e-3 * max(1.0, abs(ref)))
+            verified = bool(ok and np.all(np.diff(sc[:k] if metric != 1 else -sc[:k]) >= 0))
+        except Exception as ex:   # the oracle is optional equipment for the bench
+            verified = "unchecked: %s" % ex
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        scan_ms = prof["scan_ms_total"] / max(1, prof["scan_launches"])
+        bytes_per_launch = gs.local_n * d * es * (1 if prof["last_path"] == 2 else 1)
+        launches_per_step = prof["scan_launches"] / max(1, args.steps)
+        achieved = bytes_per_launch / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "scan_topk" if prof["last_path"] == 1 else "gemm_topk_tc",
+                "kernel_ms": scan_ms, "kernel_launches_per_step": launches_per_step,
+                "algorithmic_bytes_per_launch": bytes_per_launch}
+        if prof["last_path"] == 2:
+            flops = 2.0 * batch * gs.local_n * d
+            tf = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                    tpeak = float(json.load(fh)["bf16_tflops"])
+            except Exception:
+                tpeak = 1590.0
+            roof.update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                         "algorithmic_flops_per_launch": flops})
+        line = {
+            "metric": "brute-force top-k QPS", "value": args.steps * batch / (dev_ms * 1e-3), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ARITH[dt], "data": "synthetic",
+            "config": {"workload": describe(args.workload, n, d, dt, metric, k, batch), "rows_per_gpu": gs.local_n,
+                       "parallelism": "row-sharded x%d, one ncclAllGather of batch*k candidates" % world if world > 1 else "1 GPU",
+                       "l2_policy": "database per GPU (%.2f GB) %s L2 (126 MB)" %
+                                    (gs.local_n * d * es / 1e9, "exceeds" if gs.local_n * d * es > 126e6 else "FITS IN"),
+                       "path": "scan" if prof["last_path"] == 1 else "tensor"},
+            "e2e": {"value": args.steps * batch / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": qbytes,
+                    "d2h_bytes_per_step": batch * k * 12, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "clocks": sampler.summary(),
+            "verified_against_oracle": verified,
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                qps, cores, sample, tq = cpu_scan_qps(n, d, dt, metric, k, budget_rows=max(4096, (1 << 30) // (d * es)))
+                line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                        "sample": "%d of %d rows, %.3f s per query on the sample, scaled linearly" % (sample, n, tq)}
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+        print(json.dumps(line), flush=True)
+    gs.free()
+    eng.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,28 @@ struct Buf {
     }
     template <class T> T rd(size_t off) const { need(off, sizeof(T)); T v; std::memcpy(&v, p + off, sizeof(T)); return v; }
 };
+bool valid_utf8(const uint8_t* s, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        uint8_t c = s[i];
+        size_t extra;
+        uint32_t cp;
+        if (c < 0x80) { i++; continue; }
+        else if ((c & 0xe0) == 0xc0) { extra = 1; cp = c & 0x1f; }
+        else if ((c & 0xf0) == 0xe0) { extra = 2; cp = c & 0x0f; }
+        else if ((c & 0xf8) == 0xf0) { extra = 3; cp = c & 0x07; }
+        else return false;
+        if (i + extra >= n) return false;
+        for (size_t j = 1; j <= extra; j++) {
+            if ((s[i + j] & 0xc0) != 0x80) return false;
+            cp = (cp << 6) | (s[i + j] & 0x3f);
+        }
+        if ((extra == 1 && cp < 0x80) || (extra == 2 && cp < 0x800) || (extra == 3 && (cp < 0x10000 || cp > 0x10ffff)) ||
+            (cp >= 0xd800 && cp <= 0xdfff)) return false;
+        i += extra + 1;
+    }
+    return true;
+}
 struct Table {
     const Buf* b; size_t pos = 0, vt = 0; uint16_t vt_size = 0, tbl_size = 0;
     Table(const Buf* buf, size_t at) : b(buf), pos(at) {
@@ -123,8 +145,11 @@ struct Table {
             return std::string();
         }
         uint32_t len = b->rd<uint32_t>(t);
-        b->need(t + 4, len);
-        return std::string((const char*)b->p + t + 4, len);
+        b->need(t + 4, (size_t)len + 1);
+        const uint8_t* s = b->p + t + 4;
+        // like the flatbuffers verifier the reference runs (src/reader.rs:245): NUL-terminated, valid UTF-8
+        if (s[len] != 0 || !valid_utf8(s, len)) throw MvfError::invalid_format("Failed to parse footer: invalid string");
+        return std::string((const char*)s, len);
     }
 };
 }  // namespace

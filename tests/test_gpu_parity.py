@@ -1,0 +1,237 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar: bit-exact ids and scores for Int8/UInt8 (ties -> lowest index); floats within the tolerances
+written in tests/util.py.  All run on cuda:0 of a B200.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import metrovector_b200 as mv
+import oracle
+from util import INVALID, as_query, check_batch, check_one, f32_bits
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DT = {oracle.F32: mv.DataType.Float32, oracle.F16: mv.DataType.Float16, oracle.I8: mv.DataType.Int8, oracle.U8: mv.DataType.UInt8}
+
+
+def test_native_path_is_loaded(engine):
+    info = engine.device_info()
+    assert info["cc"][0] == 10 and info["sm_count"] >= 100
+    assert os.path.exists(mv.LIB_PATH)
+
+
+# ---- known answers from the reference's example programs, end to end through a file ------------
+def test_simple_rs_through_file(engine, golden_dir):
+    r = mv.MvfReader.open(os.path.join(golden_dir, "simple_f32.mvf"))
+    gs = engine.upload(r.vector_space("embeddings"))
+    r.close()                                   # the HBM copy outlives the mapping
+    top = mv.find_top_k_similar(gs, np.array([2.5, 4.5, 6.5, 8.5], dtype=np.float32), 3)
+    assert [t.index for t in top] == [3, 1, 4]  # ids 1 and 4 tie at 3.0 exactly -> lowest index first
+    assert [f32_bits(t.score) for t in top] == [0x3f800000, 0x40400000, 0x40400000]
+    top1 = mv.find_top_k_similar(gs, np.array([2.5, 4.5, 6.5, 8.5], dtype=np.float32), 1)
+    assert top1[0].index == 3                   # examples/simple.rs:73-94
+
+
+def test_similarity_search_rs_through_file(engine, golden_dir):
+    with open(os.path.join(golden_dir, "known_answers.json")) as fh:
+        known = json.load(fh)
+    r = mv.MvfReader.open(os.path.join(golden_dir, "clustered_f32.mvf"))
+    space = r.vector_space("clustered_data")
+    gs = engine.upload(space)
+    db = space.map_vector_range(0, 60)
+    assert np.array_equal(gs.read_rows(0, 60), db)
+    for c in known["clustered"]:
+        q = np.array(c["query"], dtype=np.float32)
+        ids, sc, isc = gs.search(q, c["k"])
+        assert ids[0].tolist() == c["ids"]      # the documented intent: k nearest, not the as-written farthest
+        assert ids[0].tolist() != c["as_written_ids"]
+        want = np.array(c["score_bits"], dtype=np.uint32).view(np.float32)
+        assert np.allclose(sc[0], want, rtol=0, atol=4e-7)    # d=4: FMA vs mul+add, at most ~1 ulp of d^2
+        check_one(db, oracle.F32, oracle.L2, q, c["k"], ids[0], sc[0], isc[0])
+
+
+def test_seeded_golden_cases(engine, golden_dir):
+    with open(os.path.join(golden_dir, "known_answers.json")) as fh:
+        known = json.load(fh)
+    cache = {}
+    for c in known["seeded"]:
+        key = (c["dtype"], c["seed"], c["n"], c["d"])
+        if key not in cache:
+            db = mv.synth_fill_host(c["dtype"], c["seed"], 0, c["n"], c["d"])
+            cache = {key: (db, engine.from_host(db, DT[c["dtype"]], mv.DistanceMetric.L2))}
+        db, gs = cache[key]
+        q = mv.synth_fill_host(c["dtype"], c["qseed"], 0, 2, c["d"])[c["qrow"]]
+        if c["planted"] is not None:
+            q = db[c["planted"]]
+        q = as_query(c["dtype"], q)
+        ids, sc, isc = gs.search(q, c["k"], metric=c["metric"])
+        if c["dtype"] in (oracle.I8, oracle.U8):
+            assert ids[0].tolist() == c["ids"]
+            if c["metric"] != oracle.COS:
+                assert isc[0].tolist() == c["iscores"]
+            else:
+                assert sc[0].view(np.uint32).tolist() == c["score_bits"]
+        else:
+            check_one(db, c["dtype"], c["metric"], q, c["k"], ids[0], sc[0], isc[0])
+            if c["planted"] is not None and c["metric"] == oracle.L2:
+                assert ids[0][0] == c["planted"] and sc[0][0] == 0.0
+
+
+# ---- sweep: dtype x metric x shapes (narrow rows, wide rows, ragged dims, k > n, batches) --------
+SHAPES = [  # (n, d)
+    (1, 1), (5, 3), (31, 4), (257, 7), (1000, 16), (999, 33), (2048, 64), (1500, 100), (3000, 128),
+    (1200, 200), (2500, 768), (700, 1000), (40, 2048),
+]
+
+
+@pytest.mark.parametrize("dtype", [oracle.F32, oracle.F16, oracle.I8, oracle.U8])
+@pytest.mark.parametrize("metric", [oracle.L2, oracle.IP, oracle.COS])
+def test_sweep_shapes(engine, dtype, metric):
+    for si, (n, d) in enumerate(SHAPES):
+        db = mv.synth_fill_host(dtype, 100 + si, 0, n, d)
+        gs = engine.from_host(db, DT[dtype], mv.DistanceMetric(metric))
+        assert gs.distance_metric == metric and gs.local_n == n
+        for nq, k in ((1, 10), (3, 1), (8, 5), (9, 40), (2, 100)):
+            qs = mv.synth_fill_host(dtype, 200 + si, 0, nq, d)
+            qs[0] = db[n // 2]                                   # a query equal to a stored row
+            queries = np.stack([as_query(dtype, r) for r in qs])
+            ids, sc, isc = gs.search(queries, k)                  # metric = the space's default
+            assert ids.shape == (nq, k)
+            check_batch(db, dtype, metric, queries, k, ids, sc, isc)
+            if k > n:
+                assert (ids[:, n:] == INVALID).all()
+        gs.free()
+
+
+def test_ties_resolve_to_lowest_index(engine):
+    # 3 distinct byte values -> thousands of exact ties in every metric
+    rng = np.random.default_rng(5)
+    for dtype, lo, hi in ((oracle.U8, 0, 3), (oracle.I8, -1, 2)):
+        for d in (16, 128, 144, 512):
+            db = rng.integers(lo, hi, (5000, d)).astype(oracle.np_dtype(dtype))
+            gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+            q = rng.integers(lo, hi, (4, d)).astype(oracle.np_dtype(dtype))
+            for metric in (oracle.L2, oracle.IP, oracle.COS):
+                ids, sc, isc = gs.search(q, 64, metric=metric)
+                check_batch(db, dtype, metric, q, 64, ids, sc, isc)
+    # float ties: duplicated rows
+    base = mv.synth_fill_host(oracle.F32, 1, 0, 50, 128)
+    db = np.concatenate([base] * 8)
+    gs = engine.from_host(db, mv.DataType.Float32, mv.DistanceMetric.L2)
+    ids, sc, _ = gs.search(base[7], 8)
+    assert ids[0].tolist() == [7 + 50 * j for j in range(8)] and (sc[0] == 0).all()
+
+
+def test_cosine_zero_norm_rows_and_query(engine):
+    db = mv.synth_fill_host(oracle.F32, 3, 0, 100, 64)
+    db[10] = 0
+    db[20] = 0
+    gs = engine.from_host(db, mv.DataType.Float32, mv.DistanceMetric.Cosine)
+    q = mv.synth_fill_host(oracle.F32, 4, 0, 1, 64)[0]
+    ids, sc, isc = gs.search(q, 100)
+    check_one(db, oracle.F32, oracle.COS, q, 100, ids[0], sc[0], isc[0])
+    pos = {int(i): float(s) for i, s in zip(ids[0], sc[0])}
+    assert pos[10] == 1.0 and pos[20] == 1.0
+    ids, sc, _ = gs.search(np.zeros(64, dtype=np.float32), 5)      # zero query: every distance is 1 -> ids 0..4
+    assert ids[0].tolist() == [0, 1, 2, 3, 4] and (sc[0] == 1.0).all()
+
+
+def test_f16_space_accepts_f16_and_f32_queries(engine):
+    db = mv.synth_fill_host(oracle.F16, 8, 0, 2000, 256)
+    gs = engine.from_host(db, mv.DataType.Float16, mv.DistanceMetric.Cosine)
+    q16 = mv.synth_fill_host(oracle.F16, 9, 0, 3, 256)
+    a = gs.search(q16, 10)
+    b = gs.search(q16.astype(np.float32), 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    check_batch(db, oracle.F16, oracle.COS, q16.astype(np.float32), 10, *a)
+
+
+def test_empty_space_and_argument_errors(engine):
+    empty = engine.from_host(np.zeros((0, 8), dtype=np.float32), mv.DataType.Float32, mv.DistanceMetric.L2)
+    ids, sc, _ = empty.search(np.ones(8, dtype=np.float32), 4)
+    assert (ids == INVALID).all() and np.isnan(sc).all()
+    db = mv.synth_fill_host(oracle.U8, 1, 0, 64, 32)
+    gs = engine.from_host(db, mv.DataType.UInt8, mv.DistanceMetric.L2)
+    q = db[:1]
+    with pytest.raises(mv.Build):
+        gs.search(q, 0)
+    with pytest.raises(mv.Build):
+        gs.search(q, 1025)
+    with pytest.raises(mv.DimensionMismatch):
+        gs.search(np.zeros((1, 31), dtype=np.uint8), 3)
+    with pytest.raises(mv.Build):
+        gs.search(q, 3, metric=7)
+    with pytest.raises(mv.Build):                                  # Custom metric is not searchable
+        engine.from_host(db, mv.DataType.UInt8, mv.DistanceMetric.Custom)
+    ids, _, isc = gs.search(q, 3)                                  # still usable after errors
+    assert ids[0][0] == 0 and isc[0][0] == 0
+
+
+# ---- residency ---------------------------------------------------------------------------------
+def test_upload_from_file_matches_mapping_and_oracle_norms(engine, golden_dir, tmp_path, monkeypatch):
+    # a file with several spaces: later blocks start at odd offsets (only 4-byte alignment is guaranteed)
+    b = mv.MvfBuilder()
+    spaces = {}
+    for name, dtype, d, n, metric in (("odd", oracle.U8, 13, 301, mv.DistanceMetric.L2),
+                                      ("f", oracle.F32, 128, 4000, mv.DistanceMetric.Cosine),
+                                      ("h", oracle.F16, 100, 3000, mv.DistanceMetric.Dot),
+                                      ("i", oracle.I8, 64, 5000, mv.DistanceMetric.Cosine)):
+        rows = mv.synth_fill_host(dtype, 77, 0, n, d)
+        spaces[name] = (dtype, rows, metric)
+        b.add_vector_space(name, d, mv.VectorType.Dense, metric, DT[dtype])
+        b.add_vectors_raw(name, rows)
+    path = str(tmp_path / "multi.mvf")
+    b.save(path)
+    for no_register in ("", "1"):
+        if no_register:
+            monkeypatch.setenv("MVF_NO_HOST_REGISTER", "1")
+        r = mv.MvfReader.open(path)
+        for name, (dtype, rows, metric) in spaces.items():
+            gs = engine.upload(r.vector_space(name))
+            assert gs.upload_stats()["path"] in ((2,) if no_register else (1, 2))
+            assert gs.local_n == rows.shape[0] and gs.distance_metric == metric
+            assert np.array_equal(gs.read_rows(0, rows.shape[0]).view(np.uint8), rows.view(np.uint8))
+            norm, sq = gs.read_norms()
+            o_norm, o_sqf, o_sqi = oracle.row_norms(rows, dtype)
+            if dtype in (oracle.I8, oracle.U8):
+                assert np.array_equal(sq.view(np.int32), o_sqi) and np.array_equal(norm, o_norm)
+            else:
+                assert np.allclose(sq, o_sqf, rtol=2e-6) and np.allclose(norm, o_norm, rtol=2e-6)
+            q = as_query(dtype, rows[17])
+            ids, sc, isc = gs.search(q, 10)
+            check_one(rows, dtype, int(metric), q, 10, ids[0], sc[0], isc[0])
+        r.close()
+
+
+def test_reference_written_f16_file_scans_what_the_reference_would(engine, golden_dir):
+    # total_vectors is halved by the reference's builder (src/builder.rs:476): its loop visits rows 0..3 only
+    r = mv.MvfReader.open(os.path.join(golden_dir, "f16_refbug.mvf"))
+    gs = engine.upload(r.vector_space("half_space"))
+    assert gs.local_n == 4 and gs.global_n == 4
+    ids, _, _ = gs.search(np.array([0.3, -0.6, 0.9, 1.0], dtype=np.float32), 8)
+    assert set(ids[0][:4].tolist()) == {0, 1, 2, 3} and (ids[0][4:] == INVALID).all()
+
+
+def test_device_generator_matches_host_generator(engine):
+    for dtype in (oracle.F32, oracle.F16, oracle.I8, oracle.U8):
+        for d in (4, 13, 128, 770):
+            gs = engine.synthetic(DT[dtype], mv.DistanceMetric.L2, 1000, d, seed=0x4D564631)
+            host = mv.synth_fill_host(dtype, 0x4D564631, 0, 1000, d)
+            assert np.array_equal(gs.read_rows(0, 1000).view(np.uint8), host.view(np.uint8))
+            assert np.array_equal(host.view(np.uint8), oracle.synth(dtype, 0x4D564631, 0, 1000, d).view(np.uint8))
+            gs.free()
+
+
+def test_profile_counters(engine):
+    gs = engine.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, 20000, 128, seed=1)
+    engine.profile(True)
+    q = mv.synth_fill_host(oracle.F32, 2, 0, 1, 128)
+    for _ in range(3):
+        gs.search(q, 10)
+    st = engine.profile_read()
+    engine.profile(False)
+    assert st["scan_launches"] == 3 and st["all_launches"] >= 6 and st["scan_ms_total"] > 0 and st["last_path"] == 1

@@ -1,0 +1,102 @@
+"""The N>1 path's host logic on CPU: world_size-2 gloo run (no GPU).
+
+What is exercised: the product's shard partition (mvf_shard_range), the packed (key << 32 | id)
+candidate words and their order-preserving key map (mvf_ordered_key_f32), one all_gather of nq*k
+words per rank, and the merge rule "ascending packed word == (score, lowest global index)".  The
+per-shard top-k itself comes from the CPU oracle here (the CUDA kernels are covered by -m gpu
+tests); the claim under test is that the sharded pipeline returns exactly the unsharded result.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import metrovector_b200 as mv
+import oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _pack(keys_u32, ids_u64):
+    return ((keys_u32.astype(np.uint64) << np.uint64(32)) | ids_u64.astype(np.uint64))
+
+
+def _worker(rank, world, port, dtype, metric, n, d, k, nq, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        begin, count = mv.shard_range(n, world, rank)
+        shard = oracle.synth(dtype, 42, begin, count, d)            # this rank regenerates only its rows
+        queries = oracle.synth(dtype, 43, 0, nq, d)
+        local = np.full((nq, k), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+        for qi in range(nq):
+            q = queries[qi].astype(np.float32) if dtype in (oracle.F32, oracle.F16) else queries[qi]
+            if count:
+                ids, sc, isc = oracle.topk(shard, dtype, metric, q, k, row_base=begin)
+                if dtype in (oracle.I8, oracle.U8) and metric != oracle.COS:
+                    v = isc.astype(np.int64) if metric == oracle.L2 else -isc.astype(np.int64)
+                    keys = (v + 2 ** 31).astype(np.uint32)
+                else:
+                    rank_val = -sc if metric == oracle.IP else sc
+                    keys = np.array([mv.ordered_key_f32(x) for x in rank_val], dtype=np.uint32)
+                local[qi, :len(ids)] = _pack(keys, ids)
+        t = torch.from_numpy(local.view(np.int64).copy())
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)                                 # the one exchange step
+        allc = np.stack([g.numpy().view(np.uint64) for g in gathered])   # [world, nq, k]
+        merged = np.sort(allc.transpose(1, 0, 2).reshape(nq, world * k), axis=1)[:, :k]
+        np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype,metric,n,d,k", [
+    (oracle.F32, oracle.L2, 1001, 24, 10),
+    (oracle.U8, oracle.L2, 777, 16, 25),      # tie-rich integers: lowest global index must win across shards
+    (oracle.F16, oracle.COS, 640, 32, 10),
+    (oracle.I8, oracle.IP, 3, 8, 5),          # fewer rows than k, one rank nearly empty
+])
+def test_two_rank_sharded_search_equals_unsharded(tmp_path, dtype, metric, n, d, k):
+    world, nq = 2, 3
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, dtype, metric, n, d, k, nq, str(tmp_path)), nprocs=world, join=True)
+    db = oracle.synth(dtype, 42, 0, n, d)
+    queries = oracle.synth(dtype, 43, 0, nq, d)
+    m0 = np.load(tmp_path / "merged_0.npy")
+    m1 = np.load(tmp_path / "merged_1.npy")
+    assert np.array_equal(m0, m1)                                    # every rank holds the same answer
+    for qi in range(nq):
+        q = queries[qi].astype(np.float32) if dtype in (oracle.F32, oracle.F16) else queries[qi]
+        ids, sc, isc = oracle.topk(db, dtype, metric, q, k)
+        got = m0[qi]
+        valid = got != np.uint64(0xFFFFFFFFFFFFFFFF)
+        assert int(valid.sum()) == len(ids)
+        assert (got[valid] & np.uint64(0xFFFFFFFF)).tolist() == ids.tolist()
+        if dtype in (oracle.F32, oracle.F16) or metric == oracle.COS:
+            back = np.array([mv.ordered_key_to_f32(int(x >> np.uint64(32))) for x in got[valid]], dtype=np.float32)
+            want = -sc if metric == oracle.IP else sc
+            assert np.array_equal(back.view(np.uint32), (want + np.float32(0)).view(np.uint32))
+
+
+def test_shard_ranges_partition_the_rows():
+    for n in (0, 1, 7, 8, 9, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for r in range(world):
+                b, c = mv.shard_range(n, world, r)
+                assert b == min(covered, n) or c == 0
+                covered += c
+            assert covered == n
+    with pytest.raises(mv.Build):
+        mv.shard_range(10, 2, 2)
