@@ -95,7 +95,8 @@ struct mvf_gpu {
     uint64_t scan_launches = 0, all_launches = 0;
     int last_path = 0;
     int ctas_per_sm_cap = 0;   // MVF_SCAN_CTAS_PER_SM, 0 = occupancy
-    DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores;
+    DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2];
+    int merge_tmp_flip = 0;
     std::map<std::pair<const void*, size_t>, int> occ_cache;
     mvf::tc::TcState tc;
 };
@@ -219,6 +220,42 @@ size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
 }
 
 void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
+    // fast flavour: the lists of one CTA staged in shared memory, two-level warp tournament; when
+    // they do not fit, a segmented pass first reduces them to a few intermediate lists
+    const size_t budget = std::min<size_t>(g->smem_optin, 200 * 1024);
+    const size_t words = budget / 8;
+    if (mp.nlists > 0 && (size_t)mp.k * (32 + 2) <= words) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(k::merge_topk_tournament, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            attr_set = true;
+        }
+        for (;;) {
+            const uint32_t nwarps = mp.nlists <= 32 ? 8u : 32u;
+            const uint32_t fit = (uint32_t)std::min<size_t>((words - (size_t)nwarps * mp.k) / mp.k, (size_t)nwarps * 32 * k::kMergeMaxHeads);
+            if (mp.nlists <= fit) {
+                mp.seg_lists = mp.nlists; mp.P = 0;
+                const size_t smem = ((size_t)mp.nlists + nwarps) * mp.k * 8;
+                k::merge_topk_tournament<<<dim3(nq, 1), nwarps * 32, smem, g->stream>>>(mp);
+                CUDA_CHECK(cudaGetLastError());
+                g->all_launches++;
+                return;
+            }
+            const uint32_t segs = (mp.nlists + fit - 1) / fit;
+            const uint32_t seg_lists = (mp.nlists + segs - 1) / segs;
+            g->merge_tmp[g->merge_tmp_flip].reserve((size_t)nq * segs * mp.k * 8);
+            k::MergeParams sp = mp;
+            sp.seg_lists = seg_lists; sp.P = 0; sp.id_add = 0;
+            sp.out_packed = (u64*)g->merge_tmp[g->merge_tmp_flip].p; sp.out_ids = nullptr; sp.out_scores = nullptr; sp.out_iscores = nullptr;
+            const size_t smem = ((size_t)seg_lists + nwarps) * mp.k * 8;
+            k::merge_topk_tournament<<<dim3(nq, segs), nwarps * 32, smem, g->stream>>>(sp);
+            CUDA_CHECK(cudaGetLastError());
+            g->all_launches++;
+            mp.in = sp.out_packed; mp.q_stride = (size_t)segs * mp.k; mp.list_stride = mp.k; mp.nlists = segs;
+            g->merge_tmp_flip ^= 1;
+        }
+    }
+    // generic flavour: rounds of block-wide bitonic sort
     const uint64_t total = (uint64_t)mp.nlists * mp.k + mp.k;
     uint32_t P = pow2ceil((uint32_t)std::min<uint64_t>(total, 16384));
     P = std::max<uint32_t>(P, std::max<uint32_t>(64, 2 * pow2ceil(mp.k)));
@@ -473,7 +510,7 @@ void mvf_gpu_shutdown(mvf_gpu* g) {
     if (g->comm) { try { nccl().CommDestroy(g->comm); } catch (...) {} }
     for (auto& e : g->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     g->cand.release(); g->packed_local.release(); g->gathered.release(); g->queries.release();
-    g->out_ids.release(); g->out_scores.release(); g->out_iscores.release();
+    g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release();
     mvf::tc::release(g->tc);
     if (g->own_stream) cudaStreamDestroy(g->stream);
     delete g;

@@ -464,7 +464,8 @@ struct MergeParams {
     const u64* in;            // candidate (q, list, j) at in[q*q_stride + list*list_stride + j]
     size_t q_stride, list_stride;
     uint32_t nlists, k;
-    uint32_t P;               // pow2 sort buffer (64-bit words), > k
+    uint32_t P;               // pow2 sort buffer (64-bit words), > k (bitonic flavour)
+    uint32_t seg_lists;       // lists per CTA (tournament flavour)
     uint32_t id_add;          // added to the low 32 bits of every valid candidate (shard row base)
     u64* out_packed;          // [nq][k] or null
     uint64_t* out_ids;        // [nq][k] or null
@@ -472,6 +473,28 @@ struct MergeParams {
     int* out_iscores;         // [nq][k] or null
     int metric, dtype;
 };
+
+// decode one merged candidate into the caller's output arrays
+__device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, uint32_t j, u64 v) {
+    const bool valid = v != kInf;
+    if (valid) v += p.id_add;
+    const size_t o = (size_t)q * p.k + j;
+    if (p.out_packed) p.out_packed[o] = v;
+    const uint32_t key = (uint32_t)(v >> 32);
+    if (p.out_ids) p.out_ids[o] = valid ? (uint64_t)(uint32_t)v : ~0ull;
+    const bool int_score = (p.dtype == DT_I8 || p.dtype == DT_U8) && p.metric != M_COS;
+    if (int_score) {
+        int s = (int)(key ^ 0x80000000u);
+        if (p.metric == M_IP) s = -s;
+        if (p.out_iscores) p.out_iscores[o] = valid ? s : 0x7fffffff;
+        if (p.out_scores) p.out_scores[o] = valid ? (float)s : __uint_as_float(0x7fc00000u);
+    } else {
+        float s = unordered_f32(key);
+        if (p.metric == M_IP) s = 0.0f - s;
+        if (p.out_iscores) p.out_iscores[o] = 0;
+        if (p.out_scores) p.out_scores[o] = valid ? s : __uint_as_float(0x7fc00000u);
+    }
+}
 
 __global__ void __launch_bounds__(1024) merge_topk(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -492,25 +515,86 @@ __global__ void __launch_bounds__(1024) merge_topk(const MergeParams p) {
         done += room;
         block_bitonic_sort(buf, (int)p.P, (int)tid, (int)blockDim.x);
     } while (done < total);
-    for (uint32_t j = tid; j < p.k; j += blockDim.x) {
-        u64 v = buf[j];
-        const bool valid = v != kInf;
-        if (valid) v += p.id_add;
-        const size_t o = (size_t)q * p.k + j;
-        if (p.out_packed) p.out_packed[o] = v;
-        const uint32_t key = (uint32_t)(v >> 32);
-        if (p.out_ids) p.out_ids[o] = valid ? (uint64_t)(uint32_t)v : ~0ull;
-        const bool int_score = (p.dtype == DT_I8 || p.dtype == DT_U8) && p.metric != M_COS;
-        if (int_score) {
-            int s = (int)(key ^ 0x80000000u);
-            if (p.metric == M_IP) s = -s;
-            if (p.out_iscores) p.out_iscores[o] = valid ? s : 0x7fffffff;
-            if (p.out_scores) p.out_scores[o] = valid ? (float)s : __uint_as_float(0x7fc00000u);
+    for (uint32_t j = tid; j < p.k; j += blockDim.x) emit_result(p, q, j, buf[j]);
+}
+
+// K3, fast flavour: the lists are individually sorted, so the k best of their union come out of a
+// two-level tournament.  All nlists*k words are staged in shared memory; each of the 32 warps
+// merges its share of the lists (one or more list heads per lane, warp-min per output), then warp 0
+// merges the 32 partial results.  ~100 cycles per output instead of a 16K-element sort.
+constexpr int kMergeMaxHeads = 4;   // list heads per lane -> up to 32*32*4 lists
+
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { u64 o = shfl_xor_u64(v, off); v = o < v ? o : v; }
+    return v;
+}
+
+// one warp merges `nl` sorted lists (list i at base + i*stride, k words each) into out[0..k)
+__device__ __forceinline__ void warp_tournament(const u64* base, size_t stride, uint32_t nl, uint32_t k, u64* out, int lane) {
+    uint32_t idx[kMergeMaxHeads];
+    u64 head[kMergeMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMergeMaxHeads; h++) {
+        idx[h] = 0;
+        const uint32_t li = (uint32_t)h * 32 + lane;
+        head[h] = li < nl ? base[(size_t)li * stride] : kInf;
+    }
+    for (uint32_t j = 0; j < k; j++) {
+        u64 mine = head[0];
+#pragma unroll
+        for (int h = 1; h < kMergeMaxHeads; h++) mine = head[h] < mine ? head[h] : mine;
+        const u64 m = warp_min_u64(mine);
+        if (m == kInf) {                                   // every list is exhausted
+            for (uint32_t t = j + lane; t < k; t += 32) out[t] = kInf;
+            break;
+        }
+        const unsigned owners = __ballot_sync(0xffffffffu, mine == m);
+        if (lane == __ffs(owners) - 1) {
+            out[j] = m;
+            bool adv = false;
+#pragma unroll
+            for (int h = 0; h < kMergeMaxHeads; h++) {
+                if (!adv && head[h] == m) {
+                    adv = true;
+                    const uint32_t li = (uint32_t)h * 32 + lane;
+                    idx[h]++;
+                    head[h] = idx[h] < k ? base[(size_t)li * stride + idx[h]] : kInf;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(1024) merge_topk_tournament(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // gridDim.y > 1: segmented pass -- CTA (q, seg) merges lists [seg*seg_lists, ...) into one
+    // intermediate sorted list at out_packed[(q*gridDim.y + seg)*k]; no decode
+    const uint32_t q = blockIdx.x, seg = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nwarps = blockDim.x >> 5;
+    const uint32_t first = seg * p.seg_lists;
+    const uint32_t nlists = first < p.nlists ? min(p.seg_lists, p.nlists - first) : 0;
+    u64* cand = reinterpret_cast<u64*>(smem);               // [nlists][k]
+    u64* lvl1 = cand + (size_t)p.seg_lists * p.k;           // [nwarps][k]
+    const u64* src = p.in + (size_t)q * p.q_stride + (size_t)first * p.list_stride;
+    const size_t total = (size_t)nlists * p.k;
+    for (size_t c = tid; c < total; c += blockDim.x) cand[c] = src[(c / p.k) * p.list_stride + (c % p.k)];
+    __syncthreads();
+    // level 1: warp w owns lists [w*per, min((w+1)*per, nlists))
+    const uint32_t per = (nlists + nwarps - 1) / nwarps;
+    const uint32_t l0 = warp * per;
+    const uint32_t nl = l0 < nlists ? min(per, nlists - l0) : 0;
+    warp_tournament(cand + (size_t)l0 * p.k, p.k, nl, p.k, lvl1 + (size_t)warp * p.k, (int)lane);
+    __syncthreads();
+    if (warp == 0) {
+        u64* out = cand;                                    // reuse: level-1 input is dead
+        warp_tournament(lvl1, p.k, nwarps, p.k, out, (int)lane);
+        if (gridDim.y > 1) {
+            u64* dst = p.out_packed + ((size_t)q * gridDim.y + seg) * p.k;
+            for (uint32_t j = lane; j < p.k; j += 32) dst[j] = out[j];
         } else {
-            float s = unordered_f32(key);
-            if (p.metric == M_IP) s = 0.0f - s;
-            if (p.out_iscores) p.out_iscores[o] = 0;
-            if (p.out_scores) p.out_scores[o] = valid ? s : __uint_as_float(0x7fc00000u);
+            for (uint32_t j = lane; j < p.k; j += 32) emit_result(p, q, j, out[j]);
         }
     }
 }

@@ -1,0 +1,71 @@
+"""Row-sharded search on N GPUs == the unsharded search == the CPU oracle.
+
+Run under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multirank_check.py
+Each rank holds its row shard (device-generated), every rank calls the same search, results are
+merged with ONE ncclAllGather of nq*k packed candidates inside the library.  Rank 0 additionally
+holds the whole database on a second, communicator-less engine and checks bit-identity.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import metrovector_b200 as mv  # noqa: E402
+import oracle  # noqa: E402
+from util import as_query, check_batch  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = mv.GpuEngine(local)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(mv.GpuEngine.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    eng.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+    solo = mv.GpuEngine(local) if rank == 0 else None
+    failures = 0
+    cases = [(0, 0, 20000, 128, 10, 3), (1, 2, 30001, 96, 10, 2), (3, 0, 50000, 128, 25, 4), (2, 1, 7, 16, 5, 2),
+             (3, 2, 40000, 64, 10, 1), (0, 1, 1000, 768, 100, 9)]
+    for dtype, metric, n, d, k, nq in cases:
+        gs = eng.synthetic(mv.DataType(dtype), mv.DistanceMetric(metric), n, d, seed=321)
+        b, c = mv.shard_range(n, world, rank)
+        assert (gs.row_base, gs.local_n, gs.global_n) == (b, c, n)
+        q = mv.synth_fill_host(dtype, 654, 0, nq, d)
+        queries = np.stack([as_query(dtype, r) for r in q])
+        ids, sc, isc = gs.search(queries, k)
+        # every rank must hold the same answer
+        t = torch.from_numpy(ids.view(np.int64).copy()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(t, ref), "ranks disagree"
+        if rank == 0:
+            db = mv.synth_fill_host(dtype, 321, 0, n, d)
+            check_batch(db, dtype, metric, queries, k, ids, sc, isc)
+            full = solo.from_host(db, mv.DataType(dtype), mv.DistanceMetric(metric))
+            ids1, sc1, isc1 = full.search(queries, k)
+            same = np.array_equal(ids, ids1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32)) and np.array_equal(isc, isc1)
+            if not same:
+                failures += 1
+                print("MISMATCH sharded vs single", (dtype, metric, n, d, k, nq))
+            full.free()
+        gs.free()
+    dist.barrier()
+    if rank == 0:
+        print("multirank ok" if failures == 0 else "multirank FAILED", "world", world)
+    eng.shutdown()
+    dist.destroy_process_group()
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
