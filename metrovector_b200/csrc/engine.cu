@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "c_api_common.hpp"
+#define MVF_ENGINE_TU
 #include "kernels.cuh"
 #include "tc_path.cuh"
 
@@ -168,48 +169,7 @@ template <int DT> size_t scan_smem(int NQ, uint32_t P, uint32_t dpad) {
     return (size_t)NQ * P * 8 + ((q_bytes + 15) & ~(size_t)15) + (size_t)NQ * sizeof(k::QueryConst) + 64;
 }
 
-template <int DT, int OP, int NQ, int R>
-void launch_scan_t(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, uint32_t* grid_out) {
-    const ScanShape sh = scan_shape<DT>(s->pitch);
-    const size_t smem = scan_smem<DT>(NQ, p.P, sh.dpad);
-    const void* fn = sh.wide ? (const void*)k::scan_topk_wide<DT, OP, NQ, R> : (const void*)k::scan_topk_narrow<DT, OP, NQ, R>;
-    int nb = occupancy(g, fn, k::kScanThreads, smem);
-    if (g->ctas_per_sm_cap > 0) nb = std::min(nb, g->ctas_per_sm_cap);
-    const uint64_t rows_per_group = sh.wide ? (uint64_t)R : (uint64_t)R * (32 / sh.LPR);
-    const uint64_t groups = (s->local_n + rows_per_group - 1) / rows_per_group;
-    uint64_t want = (groups + k::kScanWarps - 1) / k::kScanWarps;
-    uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb, want));
-    // the candidate buffer was sized by the caller with scan_grid_bound(); keep within it
-    *grid_out = grid;
-    ScanTimer t(g);
-    if (sh.wide) k::scan_topk_wide<DT, OP, NQ, R><<<grid, k::kScanThreads, smem, g->stream>>>(p);
-    else k::scan_topk_narrow<DT, OP, NQ, R><<<grid, k::kScanThreads, smem, g->stream>>>(p, sh.LPR);
-    CUDA_CHECK(cudaGetLastError());
-    g->scan_launches++; g->all_launches++;
-}
-
-template <int DT, int OP>
-void launch_scan_nq(mvf_gpu* g, const mvf_gpu_space* s, const k::ScanParams& p, int NQ, uint32_t* grid_out) {
-    switch (NQ) {
-        case 1: launch_scan_t<DT, OP, 1, 8>(g, s, p, grid_out); break;
-        case 2: launch_scan_t<DT, OP, 2, 8>(g, s, p, grid_out); break;
-        case 4: launch_scan_t<DT, OP, 4, 4>(g, s, p, grid_out); break;
-        default: launch_scan_t<DT, OP, 8, 2>(g, s, p, grid_out); break;
-    }
-}
-template <int DT>
-void launch_scan_dt(mvf_gpu* g, const mvf_gpu_space* s, const k::ScanParams& p, int NQ, uint32_t* grid_out) {
-    if (p.metric == k::M_L2) launch_scan_nq<DT, k::OP_L2>(g, s, p, NQ, grid_out);
-    else launch_scan_nq<DT, k::OP_DOT>(g, s, p, NQ, grid_out);
-}
-void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, const k::ScanParams& p, int NQ, uint32_t* grid_out) {
-    switch (s->dtype) {
-        case k::DT_F32: launch_scan_dt<k::DT_F32>(g, s, p, NQ, grid_out); break;
-        case k::DT_F16: launch_scan_dt<k::DT_F16>(g, s, p, NQ, grid_out); break;
-        case k::DT_I8: launch_scan_dt<k::DT_I8>(g, s, p, NQ, grid_out); break;
-        default: launch_scan_dt<k::DT_U8>(g, s, p, NQ, grid_out); break;
-    }
-}
+void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out);
 size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
     switch (dtype) {
         case k::DT_F32: return scan_smem<k::DT_F32>(NQ, P, scan_shape<k::DT_F32>(pitch).dpad);
@@ -217,6 +177,33 @@ size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
         case k::DT_I8: return scan_smem<k::DT_I8>(NQ, P, scan_shape<k::DT_I8>(pitch).dpad);
         default: return scan_smem<k::DT_U8>(NQ, P, scan_shape<k::DT_U8>(pitch).dpad);
     }
+}
+
+void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out) {
+    ScanShape sh;
+    const void* fn = nullptr;
+    const int op = p.metric == k::M_L2 ? k::OP_L2 : k::OP_DOT;
+    switch (s->dtype) {
+        case k::DT_F32: sh = scan_shape<k::DT_F32>(s->pitch); fn = k::scan_kernel_f32(op, NQ, sh.wide); break;
+        case k::DT_F16: sh = scan_shape<k::DT_F16>(s->pitch); fn = k::scan_kernel_f16(op, NQ, sh.wide); break;
+        case k::DT_I8: sh = scan_shape<k::DT_I8>(s->pitch); fn = k::scan_kernel_i8(op, NQ, sh.wide); break;
+        default: sh = scan_shape<k::DT_U8>(s->pitch); fn = k::scan_kernel_u8(op, NQ, sh.wide); break;
+    }
+    const size_t smem = scan_smem_any(s->dtype, NQ, p.P, s->pitch);
+    int nb = occupancy(g, fn, k::kScanThreads, smem);
+    if (g->ctas_per_sm_cap > 0) nb = std::min(nb, g->ctas_per_sm_cap);
+    const int R = k::scan_rows_in_flight(NQ);
+    const uint64_t rows_per_group = sh.wide ? (uint64_t)R : (uint64_t)R * (32 / sh.LPR);
+    const uint64_t groups = (s->local_n + rows_per_group - 1) / rows_per_group;
+    const uint64_t want = (groups + k::kScanWarps - 1) / k::kScanWarps;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb, want));
+    *grid_out = grid;
+    ScanTimer t(g);
+    int lpr = sh.LPR;
+    void* args_wide[] = {(void*)&p};
+    void* args_narrow[] = {(void*)&p, (void*)&lpr};
+    CUDA_CHECK(cudaLaunchKernel(fn, dim3(grid), dim3(k::kScanThreads), sh.wide ? args_wide : args_narrow, smem, g->stream));
+    g->scan_launches++; g->all_launches++;
 }
 
 void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
@@ -375,10 +362,16 @@ mvf_gpu_space* alloc_space(mvf_gpu* g, int dtype, int metric, uint64_t local_n, 
     s->g = g; s->dtype = dtype; s->metric = metric; s->local_n = local_n; s->row_base = row_base; s->global_n = global_n;
     s->d = d; s->pitch = (uint32_t)pitch64;
     try {
-        const size_t bytes = std::max<size_t>((size_t)local_n * s->pitch, 16);
+        // the scan kernels over-read up to one warp step past the last row instead of clamping: keep
+        // zero rows (and zero norms) behind the data
+        const size_t pad_rows = s->pitch <= 256 ? k::kPadRows : 8;
+        const size_t bytes = ((size_t)local_n + pad_rows) * s->pitch;
         CUDA_CHECK(cudaMalloc((void**)&s->rows, bytes));
-        CUDA_CHECK(cudaMalloc((void**)&s->norm, std::max<size_t>(local_n * 4, 16)));
-        CUDA_CHECK(cudaMalloc((void**)&s->sq, std::max<size_t>(local_n * 4, 16)));
+        CUDA_CHECK(cudaMalloc((void**)&s->norm, (local_n + k::kPadRows) * 4));
+        CUDA_CHECK(cudaMalloc((void**)&s->sq, (local_n + k::kPadRows) * 4));
+        CUDA_CHECK(cudaMemsetAsync(s->rows + (size_t)local_n * s->pitch, 0, pad_rows * s->pitch, g->stream));
+        CUDA_CHECK(cudaMemsetAsync(s->norm + local_n, 0, k::kPadRows * 4, g->stream));
+        CUDA_CHECK(cudaMemsetAsync(s->sq + local_n, 0, k::kPadRows * 4, g->stream));
     } catch (...) {
         cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); delete s; throw;
     }

@@ -21,6 +21,12 @@ typedef unsigned long long u64;
 constexpr u64 kInf = ~0ull;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kPadRows = 256;   // zero rows kept after the last resident row (scan kernels over-read, never clamp)
+inline int scan_rows_in_flight(int NQ) { return NQ <= 2 ? 8 : NQ == 4 ? 4 : 2; }   // R of scan_topk_*<.., NQ, R>
+const void* scan_kernel_f32(int op, int NQ, bool wide);
+const void* scan_kernel_f16(int op, int NQ, bool wide);
+const void* scan_kernel_i8(int op, int NQ, bool wide);
+const void* scan_kernel_u8(int op, int NQ, bool wide);
 
 enum { DT_F32 = 0, DT_F16 = 1, DT_I8 = 2, DT_U8 = 3 };
 enum { M_L2 = 0, M_IP = 1, M_COS = 2 };
@@ -109,9 +115,7 @@ __device__ __forceinline__ void block_bitonic_sort(u64* a, int P, int tid, int n
     __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1 -- scan_topk
-// ------------------------------------------------------------------------------------------------
+// ---- K1 parameters (kernels in scan_kernels.cuh) -------------------------------------------------
 struct ScanParams {
     const unsigned char* rows;   // resident shard, row pitch `pitch` bytes (multiple of 16, zero padded)
     const float* norm;           // sqrt(sum x^2) per row (cosine)
@@ -129,333 +133,6 @@ struct ScanParams {
 
 // per-query constants computed in the prologue
 struct QueryConst { float qnorm; int qq; };
-
-template <int DT>
-__device__ __forceinline__ u64 finalize(int metric, float facc, int iacc, int ixx, const QueryConst& qc, float xnorm,
-                                        uint32_t row) {
-    uint32_t key;
-    if (Traits<DT>::is_float) {
-        float v;
-        if (metric == M_L2) v = __fsqrt_rn(facc);
-        else if (metric == M_IP) v = 0.0f - facc;
-        else { float den = __fmul_rn(qc.qnorm, xnorm); v = den > 0.0f ? __fsub_rn(1.0f, __fdiv_rn(facc, den)) : 1.0f; }
-        key = ordered_f32(v);
-    } else {
-        if (metric == M_L2) key = ordered_i32(qc.qq + ixx - 2 * iacc);
-        else if (metric == M_IP) key = ordered_i32(-iacc);
-        else {
-            float den = __fmul_rn(qc.qnorm, xnorm);
-            float v = den > 0.0f ? __fsub_rn(1.0f, __fdiv_rn((float)iacc, den)) : 1.0f;
-            key = ordered_f32(v);
-        }
-    }
-    return ((u64)key << 32) | row;
-}
-
-// Shared prologue: stage NQ queries in shared memory (float spaces: widened to f32, chunk-split so
-// that lane-strided 16-byte reads are conflict-free; integer spaces: raw bytes), zero padded to
-// dpad components, and compute per-query constants.
-template <int DT, int NQ>
-__device__ __forceinline__ void stage_queries(const ScanParams& p, unsigned char* q_s, uint32_t dpad, QueryConst* qc_s,
-                                              float* red_s) {
-    constexpr int EPC = Traits<DT>::EPC;
-    const int tid = threadIdx.x;
-    for (int q = 0; q < NQ; q++) {
-        float fs = 0.0f; int is = 0;
-        if (Traits<DT>::is_float) {
-            float* dst = reinterpret_cast<float*>(q_s) + (size_t)q * dpad;
-            for (uint32_t j = tid; j < dpad; j += blockDim.x) {
-                float v = 0.0f;
-                if (j < p.d) {
-                    size_t qi = (size_t)(p.q0 + q) * p.d + j;
-                    v = p.qdtype == DT_F16 ? __half2float(reinterpret_cast<const __half*>(p.queries)[qi])
-                                           : reinterpret_cast<const float*>(p.queries)[qi];
-                }
-                uint32_t ci = j / EPC, e = j % EPC;
-                // f16 spaces: elements 0-3 of every chunk in the first half-plane, 4-7 in the second
-                uint32_t at = (EPC == 8) ? ((e >> 2) * (dpad / 2) + ci * 4 + (e & 3)) : j;
-                dst[at] = v;
-                fs += v * v;
-            }
-        } else {
-            unsigned char* dst = q_s + (size_t)q * dpad;
-            for (uint32_t j = tid; j < dpad; j += blockDim.x) {
-                unsigned char b = 0;
-                if (j < p.d) b = reinterpret_cast<const unsigned char*>(p.queries)[(size_t)(p.q0 + q) * p.d + j];
-                dst[j] = b;
-                int v = DT == DT_I8 ? (int)(signed char)b : (int)b;
-                is += v * v;
-            }
-        }
-        // block reduction of the norm
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            fs += __shfl_xor_sync(0xffffffffu, fs, off);
-            is += __shfl_xor_sync(0xffffffffu, is, off);
-        }
-        __syncthreads();
-        if ((tid & 31) == 0) { red_s[tid >> 5] = fs; reinterpret_cast<int*>(red_s)[kScanWarps + (tid >> 5)] = is; }
-        __syncthreads();
-        if (tid == 0) {
-            float f = 0.0f; int i = 0;
-            for (int w = 0; w < kScanWarps; w++) { f += red_s[w]; i += reinterpret_cast<int*>(red_s)[kScanWarps + w]; }
-            qc_s[q].qq = i;
-            qc_s[q].qnorm = Traits<DT>::is_float ? __fsqrt_rn(f) : __fsqrt_rn((float)i);
-        }
-    }
-    __syncthreads();
-}
-
-// accumulate one 16-byte chunk of one row against one query chunk
-template <int DT, int OP>
-__device__ __forceinline__ void accum_float(const float* xf, const float* qf, float& acc) {
-    constexpr int EPC = Traits<DT>::EPC;
-#pragma unroll
-    for (int e = 0; e < EPC; e++) {
-        if (OP == OP_L2) { float t = qf[e] - xf[e]; acc = fmaf(t, t, acc); }
-        else acc = fmaf(qf[e], xf[e], acc);
-    }
-}
-
-// CTA epilogue shared by both scan shapes: sort each query's kScanWarps*k candidates, emit best k
-template <int NQ>
-__device__ __forceinline__ void emit_cta_lists(const ScanParams& p, u64* lists) {
-    __syncthreads();
-    for (int q = 0; q < NQ; q++) {
-        u64* l = lists + (size_t)q * p.P;
-        block_bitonic_sort(l, (int)p.P, threadIdx.x, blockDim.x);
-        u64* out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
-        for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = l[j];
-    }
-}
-
-// WIDE rows (>= 32 chunks of 16 bytes): one warp per row, R rows in flight per warp.
-template <int DT, int OP, int NQ, int R>
-__global__ void __launch_bounds__(kScanThreads) scan_topk_wide(const ScanParams p) {
-    constexpr int EPC = Traits<DT>::EPC;
-    constexpr bool F = Traits<DT>::is_float;
-    extern __shared__ __align__(16) unsigned char smem[];
-    u64* lists = reinterpret_cast<u64*>(smem);
-    const uint32_t C = p.pitch >> 4, CPL = (C + 31) >> 5, dpad = CPL * 32 * EPC;
-    unsigned char* q_s = smem + (size_t)NQ * p.P * 8;
-    const size_t q_bytes = (size_t)NQ * dpad * (F ? 4 : 1);
-    QueryConst* qc_s = reinterpret_cast<QueryConst*>(q_s + ((q_bytes + 15) & ~(size_t)15));
-    float* red_s = reinterpret_cast<float*>(qc_s + NQ);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    for (uint32_t i = threadIdx.x; i < NQ * p.P; i += blockDim.x) lists[i] = kInf;
-    stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
-
-    u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) { thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; }
-
-    const uint64_t groups = (p.n + R - 1) / R;
-    for (uint64_t g = (uint64_t)blockIdx.x * kScanWarps + warp; g < groups; g += (uint64_t)gridDim.x * kScanWarps) {
-        const uint64_t row0 = g * R;
-        const unsigned char* rp[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            uint64_t row = row0 + r < p.n ? row0 + r : p.n - 1;
-            rp[r] = p.rows + row * p.pitch + (size_t)lane * 16;
-        }
-        float xn = 0.0f;
-        if (p.metric == M_COS && lane < R) xn = p.norm[row0 + lane < p.n ? row0 + lane : p.n - 1];
-        float facc[NQ][R]; int iacc[NQ][R]; int ixx[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            ixx[r] = 0;
-#pragma unroll
-            for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; }
-        }
-        for (uint32_t c = 0; c < CPL; c++) {
-            const uint32_t ci = c * 32 + lane;
-            uint4 x[R];
-            if (ci < C) {
-#pragma unroll
-                for (int r = 0; r < R; r++) x[r] = ldg_stream16(rp[r] + (size_t)c * 512);
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) x[r] = make_uint4(0, 0, 0, 0);
-            }
-            if (F) {
-                float xf[R][EPC];
-#pragma unroll
-                for (int r = 0; r < R; r++) widen<DT>(x[r], xf[r]);
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    float qf[EPC];
-                    const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
-                    float4 a = reinterpret_cast<const float4*>(qb)[ci];
-                    qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w;
-                    if (EPC == 8) {
-                        float4 b = reinterpret_cast<const float4*>(qb + dpad / 2)[ci];
-                        qf[4] = b.x; qf[5] = b.y; qf[6] = b.z; qf[7] = b.w;
-                    }
-#pragma unroll
-                    for (int r = 0; r < R; r++) accum_float<DT, OP>(xf[r], qf, facc[q][r]);
-                }
-            } else {
-                if (OP == OP_L2) {
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        ixx[r] = dp4<DT>(x[r].x, x[r].x, ixx[r]); ixx[r] = dp4<DT>(x[r].y, x[r].y, ixx[r]);
-                        ixx[r] = dp4<DT>(x[r].z, x[r].z, ixx[r]); ixx[r] = dp4<DT>(x[r].w, x[r].w, ixx[r]);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    uint4 qv = reinterpret_cast<const uint4*>(q_s + (size_t)q * dpad)[ci];
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        int a = iacc[q][r];
-                        a = dp4<DT>(qv.x, x[r].x, a); a = dp4<DT>(qv.y, x[r].y, a);
-                        a = dp4<DT>(qv.z, x[r].z, a); a = dp4<DT>(qv.w, x[r].w, a);
-                        iacc[q][r] = a;
-                    }
-                }
-            }
-        }
-        // warp reductions: every lane ends with the row totals
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                if (!F && OP == OP_L2) ixx[r] += __shfl_xor_sync(0xffffffffu, ixx[r], off);
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    if (F) facc[q][r] += __shfl_xor_sync(0xffffffffu, facc[q][r], off);
-                    else iacc[q][r] += __shfl_xor_sync(0xffffffffu, iacc[q][r], off);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (row0 + r >= p.n) break;
-            float xnr = __shfl_sync(0xffffffffu, xn, r);
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                u64 pk = finalize<DT>(p.metric, facc[q][r], iacc[q][r], ixx[r], qc[q], xnr, (uint32_t)(row0 + r));
-                if (pk < thr[q]) list_insert(lists + (size_t)q * p.P + warp * p.k, (int)p.k, pk, thr[q], pos[q], lane);
-            }
-        }
-    }
-    emit_cta_lists<NQ>(p, lists);
-}
-
-// NARROW rows (<= 16 chunks): LPR = pow2 >= chunks lanes per row, 32/LPR rows per warp load,
-// R loads in flight.  The lane's query chunk never changes, so it lives in registers.
-template <int DT, int OP, int NQ, int R>
-__global__ void __launch_bounds__(kScanThreads) scan_topk_narrow(const ScanParams p, const int LPR) {
-    constexpr int EPC = Traits<DT>::EPC;
-    constexpr bool F = Traits<DT>::is_float;
-    extern __shared__ __align__(16) unsigned char smem[];
-    u64* lists = reinterpret_cast<u64*>(smem);
-    const uint32_t C = p.pitch >> 4, dpad = (uint32_t)LPR * EPC;
-    unsigned char* q_s = smem + (size_t)NQ * p.P * 8;
-    const size_t q_bytes = (size_t)NQ * dpad * (F ? 4 : 1);
-    QueryConst* qc_s = reinterpret_cast<QueryConst*>(q_s + ((q_bytes + 15) & ~(size_t)15));
-    float* red_s = reinterpret_cast<float*>(qc_s + NQ);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int li = lane & (LPR - 1), ri = lane / LPR, RPW = 32 / LPR;
-
-    for (uint32_t i = threadIdx.x; i < NQ * p.P; i += blockDim.x) lists[i] = kInf;
-    stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
-
-    u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
-    float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q];
-        if (F) {
-            const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
-            float4 a = reinterpret_cast<const float4*>(qb)[li];
-            qf[q][0] = a.x; qf[q][1] = a.y; qf[q][2] = a.z; qf[q][3] = a.w;
-            if (EPC == 8) {
-                float4 b = reinterpret_cast<const float4*>(qb + dpad / 2)[li];
-                qf[q][4 % (F ? EPC : 1)] = b.x; qf[q][5 % (F ? EPC : 1)] = b.y;
-                qf[q][6 % (F ? EPC : 1)] = b.z; qf[q][7 % (F ? EPC : 1)] = b.w;
-            }
-            qv[q] = make_uint4(0, 0, 0, 0);
-        } else {
-            qv[q] = reinterpret_cast<const uint4*>(q_s + (size_t)q * dpad)[li];
-        }
-    }
-    const bool active = (uint32_t)li < C;
-    const uint64_t rows_per_step = (uint64_t)R * RPW;
-    const uint64_t groups = (p.n + rows_per_step - 1) / rows_per_step;
-    for (uint64_t g = (uint64_t)blockIdx.x * kScanWarps + warp; g < groups; g += (uint64_t)gridDim.x * kScanWarps) {
-        const uint64_t row0 = g * rows_per_step;
-        uint4 x[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            uint64_t row = row0 + (uint64_t)r * RPW + ri;
-            if (row >= p.n) row = p.n - 1;
-            x[r] = active ? ldg_stream16(p.rows + row * p.pitch + (size_t)li * 16) : make_uint4(0, 0, 0, 0);
-        }
-        float xn[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            xn[r] = 0.0f;
-            if (p.metric == M_COS) {
-                uint64_t row = row0 + (uint64_t)r * RPW + ri;
-                xn[r] = p.norm[row < p.n ? row : p.n - 1];
-            }
-        }
-        float facc[NQ][R]; int iacc[NQ][R]; int ixx[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            ixx[r] = 0;
-            if (F) {
-                float xf[EPC];
-                widen<DT>(x[r], xf);
-#pragma unroll
-                for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; accum_float<DT, OP>(xf, qf[q], facc[q][r]); }
-            } else {
-                if (OP == OP_L2) {
-                    ixx[r] = dp4<DT>(x[r].x, x[r].x, ixx[r]); ixx[r] = dp4<DT>(x[r].y, x[r].y, ixx[r]);
-                    ixx[r] = dp4<DT>(x[r].z, x[r].z, ixx[r]); ixx[r] = dp4<DT>(x[r].w, x[r].w, ixx[r]);
-                }
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    int a = 0;
-                    a = dp4<DT>(qv[q].x, x[r].x, a); a = dp4<DT>(qv[q].y, x[r].y, a);
-                    a = dp4<DT>(qv[q].z, x[r].z, a); a = dp4<DT>(qv[q].w, x[r].w, a);
-                    iacc[q][r] = a; facc[q][r] = 0.0f;
-                }
-            }
-        }
-        for (int off = LPR >> 1; off > 0; off >>= 1) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (!F && OP == OP_L2) ixx[r] += __shfl_xor_sync(0xffffffffu, ixx[r], off);
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    if (F) facc[q][r] += __shfl_xor_sync(0xffffffffu, facc[q][r], off);
-                    else iacc[q][r] += __shfl_xor_sync(0xffffffffu, iacc[q][r], off);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const uint64_t row = row0 + (uint64_t)r * RPW + ri;
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                u64 pk = kInf;
-                if (row < p.n && li == 0)
-                    pk = finalize<DT>(p.metric, facc[q][r], iacc[q][r], ixx[r], qc[q], xn[r], (uint32_t)row);
-                unsigned hits = __ballot_sync(0xffffffffu, pk < thr[q]);
-                while (hits) {
-                    int src = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    u64 c = shfl_u64(pk, src);
-                    if (c < thr[q]) list_insert(lists + (size_t)q * p.P + warp * p.k, (int)p.k, c, thr[q], pos[q], lane);
-                }
-            }
-        }
-    }
-    emit_cta_lists<NQ>(p, lists);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K3 -- merge_topk: one CTA per query merges `nlists` lists of k candidates; optionally decodes.
@@ -496,6 +173,7 @@ __device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, ui
     }
 }
 
+#ifdef MVF_ENGINE_TU   // non-template kernels: defined in engine.cu's translation unit only
 __global__ void __launch_bounds__(1024) merge_topk(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     u64* buf = reinterpret_cast<u64*>(smem);
@@ -598,6 +276,8 @@ __global__ void __launch_bounds__(1024) merge_topk_tournament(const MergeParams 
         }
     }
 }
+
+#endif  // MVF_ENGINE_TU
 
 // ------------------------------------------------------------------------------------------------
 // K0 -- row norms (once per resident space): norm = sqrt(sum x^2) (f32), sq = sum x^2 (f32, or the

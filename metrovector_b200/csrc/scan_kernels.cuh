@@ -1,0 +1,456 @@
+// scan_kernels.cuh -- K1, the bandwidth-bound scan with fused top-k (templates; instantiated per
+// data type in scan_f32.cu / scan_f16.cu / scan_i8.cu / scan_u8.cu so the build parallelises).
+#pragma once
+#include "kernels.cuh"
+
+namespace mvf {
+namespace k {
+
+// ------------------------------------------------------------------------------------------------
+// K1 -- scan_topk
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ u64 finalize(int metric, float facc, int iacc, int ixx, const QueryConst& qc, float xnorm,
+                                        uint32_t row) {
+    uint32_t key;
+    if (Traits<DT>::is_float) {
+        float v;
+        if (metric == M_L2) v = __fsqrt_rn(facc);
+        else if (metric == M_IP) v = 0.0f - facc;
+        else { float den = __fmul_rn(qc.qnorm, xnorm); v = den > 0.0f ? __fsub_rn(1.0f, __fdiv_rn(facc, den)) : 1.0f; }
+        key = ordered_f32(v);
+    } else {
+        if (metric == M_L2) key = ordered_i32(qc.qq + ixx - 2 * iacc);
+        else if (metric == M_IP) key = ordered_i32(-iacc);
+        else {
+            float den = __fmul_rn(qc.qnorm, xnorm);
+            float v = den > 0.0f ? __fsub_rn(1.0f, __fdiv_rn((float)iacc, den)) : 1.0f;
+            key = ordered_f32(v);
+        }
+    }
+    return ((u64)key << 32) | row;
+}
+
+// Shared prologue: stage NQ queries in shared memory (float spaces: widened to f32, chunk-split so
+// that lane-strided 16-byte reads are conflict-free; integer spaces: raw bytes), zero padded to
+// dpad components, and compute per-query constants.
+template <int DT, int NQ>
+__device__ __forceinline__ void stage_queries(const ScanParams& p, unsigned char* q_s, uint32_t dpad, QueryConst* qc_s,
+                                              float* red_s) {
+    constexpr int EPC = Traits<DT>::EPC;
+    const int tid = threadIdx.x;
+    for (int q = 0; q < NQ; q++) {
+        float fs = 0.0f; int is = 0;
+        if (Traits<DT>::is_float) {
+            float* dst = reinterpret_cast<float*>(q_s) + (size_t)q * dpad;
+            for (uint32_t j = tid; j < dpad; j += blockDim.x) {
+                float v = 0.0f;
+                if (j < p.d) {
+                    size_t qi = (size_t)(p.q0 + q) * p.d + j;
+                    v = p.qdtype == DT_F16 ? __half2float(reinterpret_cast<const __half*>(p.queries)[qi])
+                                           : reinterpret_cast<const float*>(p.queries)[qi];
+                }
+                uint32_t ci = j / EPC, e = j % EPC;
+                // f16 spaces: elements 0-3 of every chunk in the first half-plane, 4-7 in the second
+                uint32_t at = (EPC == 8) ? ((e >> 2) * (dpad / 2) + ci * 4 + (e & 3)) : j;
+                dst[at] = v;
+                fs += v * v;
+            }
+        } else {
+            unsigned char* dst = q_s + (size_t)q * dpad;
+            for (uint32_t j = tid; j < dpad; j += blockDim.x) {
+                unsigned char b = 0;
+                if (j < p.d) b = reinterpret_cast<const unsigned char*>(p.queries)[(size_t)(p.q0 + q) * p.d + j];
+                dst[j] = b;
+                int v = DT == DT_I8 ? (int)(signed char)b : (int)b;
+                is += v * v;
+            }
+        }
+        // block reduction of the norm
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            fs += __shfl_xor_sync(0xffffffffu, fs, off);
+            is += __shfl_xor_sync(0xffffffffu, is, off);
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { red_s[tid >> 5] = fs; reinterpret_cast<int*>(red_s)[kScanWarps + (tid >> 5)] = is; }
+        __syncthreads();
+        if (tid == 0) {
+            float f = 0.0f; int i = 0;
+            for (int w = 0; w < kScanWarps; w++) { f += red_s[w]; i += reinterpret_cast<int*>(red_s)[kScanWarps + w]; }
+            qc_s[q].qq = i;
+            qc_s[q].qnorm = Traits<DT>::is_float ? __fsqrt_rn(f) : __fsqrt_rn((float)i);
+        }
+    }
+    __syncthreads();
+}
+
+// accumulate one 16-byte chunk of one row against one query chunk
+template <int DT, int OP>
+__device__ __forceinline__ void accum_float(const float* xf, const float* qf, float& acc) {
+    constexpr int EPC = Traits<DT>::EPC;
+#pragma unroll
+    for (int e = 0; e < EPC; e++) {
+        if (OP == OP_L2) { float t = qf[e] - xf[e]; acc = fmaf(t, t, acc); }
+        else acc = fmaf(qf[e], xf[e], acc);
+    }
+}
+
+// CTA epilogue shared by both scan shapes: sort each query's kScanWarps*k candidates, emit best k
+template <int NQ>
+__device__ __forceinline__ void emit_cta_lists(const ScanParams& p, u64* lists) {
+    __syncthreads();
+    for (int q = 0; q < NQ; q++) {
+        u64* l = lists + (size_t)q * p.P;
+        block_bitonic_sort(l, (int)p.P, threadIdx.x, blockDim.x);
+        u64* out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
+        for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = l[j];
+    }
+}
+
+// Transposed warp reduction.  Every lane enters with R partial sums (one per row of the group);
+// the lanes of each LPR-lane team leave with the team totals spread over them: while more than one
+// value is left, a step at offset OFF halves the value count (each lane keeps the half selected
+// by its lane bit and receives the partner's share of it), afterwards plain butterfly steps.
+// Cost: R-1 + log2(LPR/R) shuffles instead of R*log2(LPR).  `rbase` returns the row (0..R) of
+// the lane's value 0; values p = 0..CNT-1 belong to rows rbase + p, CNT = max(1, R/LPR).
+template <int CNT, int OFF, class T, int R>
+__device__ __forceinline__ void reduce_step(T (&v)[R], int lane, int& rbase) {
+    if constexpr (OFF >= 1) {
+        if constexpr (CNT > 1) {
+            constexpr int H = CNT / 2;
+            const bool up = (lane & OFF) != 0;
+#pragma unroll
+            for (int i = 0; i < H; i++) {
+                const T send = up ? v[i] : v[i + H];
+                const T keep = up ? v[i + H] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+            }
+            if (up) rbase += H;
+            reduce_step<H, OFF / 2>(v, lane, rbase);
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+            reduce_step<1, OFF / 2>(v, lane, rbase);
+        }
+    }
+}
+template <int R, int LPR, class T>
+__device__ __forceinline__ int reduce_rows(T (&v)[R], int lane) {
+    int rbase = 0;
+    reduce_step<R, LPR / 2>(v, lane, rbase);
+    return rbase;
+}
+template <int R, int LPR> struct RowsLeft { static constexpr int CNT = (R / LPR) > 1 ? (R / LPR) : 1; static constexpr int DUP = LPR > R ? LPR / R : 1; };
+
+// offer the candidates held by the lanes of a warp (kInf = nothing) to the warp's running list
+__device__ __forceinline__ void offer(u64 pk, u64* list, int k, u64& thr, int& pos, int lane) {
+    unsigned hits = __ballot_sync(0xffffffffu, pk < thr);
+    while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const u64 c = shfl_u64(pk, src);
+        if (c < thr) list_insert(list, k, c, thr, pos, lane);
+    }
+}
+
+// WIDE rows (> 16 chunks of 16 bytes): one warp per row, R consecutive rows per warp step.
+// Loads are software-pipelined in registers: each 16-byte register tile is refilled with the
+// next chunk (or the next row group's first chunk) right after it is consumed, so every lane keeps
+// R loads in flight all the time.  The resident buffer carries kPadRows zero rows past the end
+// (engine.cu), so the last partial group needs no clamping; rows >= n are dropped before insert.
+template <int DT, int OP, int NQ, int R>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanParams p) {
+    constexpr int EPC = Traits<DT>::EPC;
+    constexpr bool F = Traits<DT>::is_float;
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64* lists = reinterpret_cast<u64*>(smem);
+    const uint32_t C = p.pitch >> 4, CPL = (C + 31) >> 5, dpad = CPL * 32 * EPC;
+    unsigned char* q_s = smem + (size_t)NQ * p.P * 8;
+    const size_t q_bytes = (size_t)NQ * dpad * (F ? 4 : 1);
+    QueryConst* qc_s = reinterpret_cast<QueryConst*>(q_s + ((q_bytes + 15) & ~(size_t)15));
+    float* red_s = reinterpret_cast<float*>(qc_s + NQ);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (uint32_t i = threadIdx.x; i < NQ * p.P; i += blockDim.x) lists[i] = kInf;
+    stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
+
+    u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; }
+
+    const uint32_t n = (uint32_t)p.n;
+    const uint32_t pitch = p.pitch;
+    const bool ragged = (C & 31) != 0;
+    const unsigned char* lane_base = p.rows + (size_t)lane * 16;
+    int myrow;
+    {   // which row of a group this lane reports after the transposed reduction
+        float t[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) t[r] = 0.f;
+        myrow = reduce_rows<R, 32>(t, lane);
+    }
+    const bool reporter = (lane & (RowsLeft<R, 32>::DUP - 1)) == 0;
+
+    const uint32_t groups = (uint32_t)(((uint64_t)n + R - 1) / R), gstride = gridDim.x * kScanWarps;
+    uint32_t g = blockIdx.x * kScanWarps + warp;
+    const unsigned char* ptr = lane_base;
+    uint4 x[R];
+    float xn = 0.0f;
+    if (g < groups) {
+        ptr = lane_base + (size_t)g * R * pitch;
+#pragma unroll
+        for (int r = 0; r < R; r++) x[r] = ldg_stream16(ptr + (size_t)r * pitch);
+        if (p.metric == M_COS) xn = p.norm[g * R + myrow];
+    }
+    while (g < groups) {
+        const uint32_t gn = g + gstride;
+        const bool more = gn < groups && gn > g;
+        // the refill is unconditional (a predicated load would force register copies): after the
+        // last group it just re-reads the current one
+        const unsigned char* ptr_n = more ? lane_base + (size_t)gn * R * pitch : ptr;
+        float xn_n = 0.0f;
+        if (p.metric == M_COS && more) xn_n = p.norm[gn * R + myrow];
+        float facc[NQ][R]; int iacc[NQ][R]; int ixx[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            ixx[r] = 0;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; }
+        }
+        for (uint32_t c = 0; c < CPL; c++) {
+            const bool lastc = c + 1 == CPL;
+            const unsigned char* tp = lastc ? ptr_n : ptr + (size_t)(c + 1) * 512;
+            const uint32_t ci = c * 32 + lane;
+            // ragged rows: lanes past the row end read whatever follows (always inside the padded
+            // buffer) and the tile is zeroed when consumed
+            const bool dead = ragged && ci >= C;
+            float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                if (F) {
+                    const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
+                    float4 a = reinterpret_cast<const float4*>(qb)[ci];
+                    qf[q][0] = a.x; qf[q][1 % EPC] = a.y; qf[q][2 % EPC] = a.z; qf[q][3 % EPC] = a.w;
+                    if (EPC == 8) {
+                        float4 b = reinterpret_cast<const float4*>(qb + dpad / 2)[ci];
+                        qf[q][4 % EPC] = b.x; qf[q][5 % EPC] = b.y; qf[q][6 % EPC] = b.z; qf[q][7 % EPC] = b.w;
+                    }
+                } else {
+                    qv[q] = reinterpret_cast<const uint4*>(q_s + (size_t)q * dpad)[ci];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                uint4 cur = x[r];
+                x[r] = ldg_stream16(tp + (size_t)r * pitch);
+                if (dead) cur = make_uint4(0, 0, 0, 0);
+                if (F) {
+                    float xf[EPC];
+                    widen<DT>(cur, xf);
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) accum_float<DT, OP>(xf, qf[q], facc[q][r]);
+                } else {
+                    if (OP == OP_L2) {
+                        ixx[r] = dp4<DT>(cur.x, cur.x, ixx[r]); ixx[r] = dp4<DT>(cur.y, cur.y, ixx[r]);
+                        ixx[r] = dp4<DT>(cur.z, cur.z, ixx[r]); ixx[r] = dp4<DT>(cur.w, cur.w, ixx[r]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        int a = iacc[q][r];
+                        a = dp4<DT>(qv[q].x, cur.x, a); a = dp4<DT>(qv[q].y, cur.y, a);
+                        a = dp4<DT>(qv[q].z, cur.z, a); a = dp4<DT>(qv[q].w, cur.w, a);
+                        iacc[q][r] = a;
+                    }
+                }
+            }
+        }
+        // transposed reductions: one row total per lane, then one finalize per lane
+        const uint32_t row = g * R + myrow;
+        const bool mine = reporter && row < n;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            float fv = 0.0f; int iv = 0;
+            if (F) { reduce_rows<R, 32>(facc[q], lane); fv = facc[q][0]; }
+            else {
+                if (OP == OP_L2) {   // ||x||^2 - 2 q.x reduces as one value
+#pragma unroll
+                    for (int r = 0; r < R; r++) iacc[q][r] = ixx[r] - 2 * iacc[q][r];
+                }
+                reduce_rows<R, 32>(iacc[q], lane); iv = iacc[q][0];
+            }
+            u64 pk = kInf;
+            if (mine) {
+                if (!F && OP == OP_L2) pk = ((u64)ordered_i32(qc[q].qq + iv) << 32) | row;
+                else pk = finalize<DT>(p.metric, fv, iv, 0, qc[q], xn, row);
+            }
+            offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane);
+        }
+        g = more ? gn : groups; ptr = ptr_n; xn = xn_n;
+    }
+    emit_cta_lists<NQ>(p, lists);
+}
+
+// NARROW rows (<= 16 chunks): LPR = pow2 >= chunks lanes per row, 32/LPR rows per warp load,
+// R loads in flight per lane (software-pipelined like the wide kernel).  The lane's query chunk
+// never changes, so it lives in registers.
+template <int DT, int OP, int NQ, int R, int LPR>
+__device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, const unsigned char* q_s, uint32_t dpad,
+                                            const QueryConst* qc_s) {
+    constexpr int EPC = Traits<DT>::EPC;
+    constexpr bool F = Traits<DT>::is_float;
+    constexpr int RPW = 32 / LPR, CNT = RowsLeft<R, LPR>::CNT, DUP = RowsLeft<R, LPR>::DUP;
+    constexpr uint32_t RPS = (uint32_t)R * RPW;                 // rows per warp step (<= kPadRows)
+    const uint32_t C = p.pitch >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int li = lane & (LPR - 1), ri = lane / LPR;
+
+    u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
+    float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q];
+        if (F) {
+            const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
+            float4 a = reinterpret_cast<const float4*>(qb)[li];
+            qf[q][0] = a.x; qf[q][1 % EPC] = a.y; qf[q][2 % EPC] = a.z; qf[q][3 % EPC] = a.w;
+            if (EPC == 8) {
+                float4 b = reinterpret_cast<const float4*>(qb + dpad / 2)[li];
+                qf[q][4 % EPC] = b.x; qf[q][5 % EPC] = b.y; qf[q][6 % EPC] = b.z; qf[q][7 % EPC] = b.w;
+            }
+            qv[q] = make_uint4(0, 0, 0, 0);
+        } else {
+            qv[q] = reinterpret_cast<const uint4*>(q_s + (size_t)q * dpad)[li];
+        }
+    }
+    const uint32_t n = (uint32_t)p.n;
+    const uint32_t pitch = p.pitch;
+    const bool active = (uint32_t)li < C;
+    // lane's first row inside a step and its byte offset; row r of the step adds r*RPW rows
+    const unsigned char* lane_base = p.rows + (size_t)ri * pitch + (size_t)li * 16;
+    const uint32_t step_pitch = (uint32_t)RPW * pitch;
+    int myr;
+    {
+        float t[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) t[r] = 0.f;
+        myr = reduce_rows<R, LPR>(t, li);
+    }
+    const bool reporter = (li & (DUP - 1)) == 0;
+
+    const uint32_t groups = (uint32_t)(((uint64_t)n + RPS - 1) / RPS), gstride = gridDim.x * kScanWarps;
+    uint32_t g = blockIdx.x * kScanWarps + warp;
+    uint4 x[R];
+    float xn[CNT];
+#pragma unroll
+    for (int c = 0; c < CNT; c++) xn[c] = 0.0f;
+    if (g < groups) {
+        const unsigned char* ptr = lane_base + (size_t)g * RPS * pitch;
+#pragma unroll
+        for (int r = 0; r < R; r++) x[r] = ldg_stream16(ptr + (size_t)r * step_pitch);
+        if (p.metric == M_COS) {
+#pragma unroll
+            for (int c = 0; c < CNT; c++) {
+                uint32_t row = g * RPS + (uint32_t)(myr + c) * RPW + ri;
+                xn[c] = p.norm[row < n ? row : n - 1];
+            }
+        }
+    }
+    while (g < groups) {
+        const uint32_t gn = g + gstride;
+        const bool more = gn < groups && gn > g;
+        const unsigned char* ptr_n = lane_base + (size_t)(more ? gn : g) * RPS * pitch;   // unconditional refill
+        float xn_n[CNT];
+#pragma unroll
+        for (int c = 0; c < CNT; c++) {
+            xn_n[c] = 0.0f;
+            if (p.metric == M_COS && more) {
+                uint32_t row = gn * RPS + (uint32_t)(myr + c) * RPW + ri;
+                xn_n[c] = p.norm[row < n ? row : n - 1];
+            }
+        }
+        float facc[NQ][R]; int iacc[NQ][R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint4 cur = x[r];
+            x[r] = ldg_stream16(ptr_n + (size_t)r * step_pitch);
+            if (!active) cur = make_uint4(0, 0, 0, 0);
+            if (F) {
+                float xf[EPC];
+                widen<DT>(cur, xf);
+#pragma unroll
+                for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; accum_float<DT, OP>(xf, qf[q], facc[q][r]); }
+            } else {
+                int xx = 0;
+                if (OP == OP_L2) {
+                    xx = dp4<DT>(cur.x, cur.x, xx); xx = dp4<DT>(cur.y, cur.y, xx);
+                    xx = dp4<DT>(cur.z, cur.z, xx); xx = dp4<DT>(cur.w, cur.w, xx);
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    int a = 0;
+                    a = dp4<DT>(qv[q].x, cur.x, a); a = dp4<DT>(qv[q].y, cur.y, a);
+                    a = dp4<DT>(qv[q].z, cur.z, a); a = dp4<DT>(qv[q].w, cur.w, a);
+                    iacc[q][r] = OP == OP_L2 ? xx - 2 * a : a; facc[q][r] = 0.0f;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            if (F) reduce_rows<R, LPR>(facc[q], li); else reduce_rows<R, LPR>(iacc[q], li);
+#pragma unroll
+            for (int c = 0; c < CNT; c++) {
+                const uint32_t row = g * RPS + (uint32_t)(myr + c) * RPW + ri;
+                u64 pk = kInf;
+                if (reporter && row < n) {
+                    if (!F && OP == OP_L2) pk = ((u64)ordered_i32(qc[q].qq + iacc[q][c]) << 32) | row;
+                    else pk = finalize<DT>(p.metric, facc[q][c], iacc[q][c], 0, qc[q], xn[c], row);
+                }
+                offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane);
+            }
+        }
+        g = more ? gn : groups;
+#pragma unroll
+        for (int c = 0; c < CNT; c++) xn[c] = xn_n[c];
+    }
+}
+
+template <int DT, int OP, int NQ, int R>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_narrow(const ScanParams p, const int LPR) {
+    constexpr int EPC = Traits<DT>::EPC;
+    constexpr bool F = Traits<DT>::is_float;
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64* lists = reinterpret_cast<u64*>(smem);
+    const uint32_t dpad = (uint32_t)LPR * EPC;
+    unsigned char* q_s = smem + (size_t)NQ * p.P * 8;
+    const size_t q_bytes = (size_t)NQ * dpad * (F ? 4 : 1);
+    QueryConst* qc_s = reinterpret_cast<QueryConst*>(q_s + ((q_bytes + 15) & ~(size_t)15));
+    float* red_s = reinterpret_cast<float*>(qc_s + NQ);
+    for (uint32_t i = threadIdx.x; i < NQ * p.P; i += blockDim.x) lists[i] = kInf;
+    stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
+    switch (LPR) {
+        case 1: narrow_body<DT, OP, NQ, R, 1>(p, lists, q_s, dpad, qc_s); break;
+        case 2: narrow_body<DT, OP, NQ, R, 2>(p, lists, q_s, dpad, qc_s); break;
+        case 4: narrow_body<DT, OP, NQ, R, 4>(p, lists, q_s, dpad, qc_s); break;
+        case 8: narrow_body<DT, OP, NQ, R, 8>(p, lists, q_s, dpad, qc_s); break;
+        default: narrow_body<DT, OP, NQ, R, 16>(p, lists, q_s, dpad, qc_s); break;
+    }
+    emit_cta_lists<NQ>(p, lists);
+}
+
+// kernel lookup for one data type (called from engine.cu through scan_kernel_for())
+template <int DT, int OP>
+inline const void* scan_kernel_op(int NQ, bool wide) {
+    switch (NQ) {
+        case 1: return wide ? (const void*)scan_topk_wide<DT, OP, 1, 8> : (const void*)scan_topk_narrow<DT, OP, 1, 8>;
+        case 2: return wide ? (const void*)scan_topk_wide<DT, OP, 2, 8> : (const void*)scan_topk_narrow<DT, OP, 2, 8>;
+        case 4: return wide ? (const void*)scan_topk_wide<DT, OP, 4, 4> : (const void*)scan_topk_narrow<DT, OP, 4, 4>;
+        default: return wide ? (const void*)scan_topk_wide<DT, OP, 8, 2> : (const void*)scan_topk_narrow<DT, OP, 8, 2>;
+    }
+}
+template <int DT>
+inline const void* scan_kernel_dt(int op, int NQ, bool wide) {
+    return op == OP_L2 ? scan_kernel_op<DT, OP_L2>(NQ, wide) : scan_kernel_op<DT, OP_DOT>(NQ, wide);
+}
+
+}  // namespace k
+}  // namespace mvf
