@@ -191,6 +191,10 @@ MVF_API int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtyp
 MVF_API int mvf_gpu_search_device(mvf_gpu_space* s, const void* d_queries, int query_dtype,
                                   uint32_t nq, uint32_t k, int metric, uint64_t* d_out_ids,
                                   float* d_out_scores, int32_t* d_out_iscores);
+/* test hook for the tensor-core path: runs K2 and copies back the raw ranking values it selected
+ * on (padded to 128 queries x 256 rows tiles); out holds out_elems floats */
+MVF_API int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq, uint32_t k,
+                            int metric, float* out, uint64_t out_elems, uint32_t* out_rows, uint32_t* out_cols);
 /* path selection: 0 auto, 1 bandwidth scan (K1), 2 tensor-core contraction (K2) */
 MVF_API int mvf_gpu_set_path(mvf_gpu* g, int path);
 /* instrumentation: when enabled, searches bracket the dominant kernel with CUDA events on the

@@ -135,6 +135,7 @@ _SIGS = {
     "mvf_gpu_space_read_norms": [_P, _P, _P],
     "mvf_gpu_search": [_P, _P, _INT, _U32, _U32, _INT, _P, _P, _P],
     "mvf_gpu_search_device": [_P, _P, _INT, _U32, _U32, _INT, _P, _P, _P],
+    "mvf_gpu_tc_dump": [_P, _P, _INT, _U32, _U32, _INT, _P, _U64, _c.POINTER(_U32), _c.POINTER(_U32)],
     "mvf_gpu_set_path": [_P, _INT],
     "mvf_gpu_profile": [_P, _INT],
     "mvf_gpu_profile_read": [_P, _c.POINTER(_c.c_double), _c.POINTER(_U64), _c.POINTER(_U64), _c.POINTER(_INT)],
@@ -504,6 +505,19 @@ class GpuSpace:
         _check(_lib.mvf_gpu_search(self._h, q.ctypes.data_as(_P), int(qd), nq, k, -1 if metric is None else int(metric),
                                    ids.ctypes.data_as(_P), scores.ctypes.data_as(_P), iscores.ctypes.data_as(_P)))
         return ids, scores, iscores
+
+    def tc_dump(self, queries, k=10, metric=None):
+        """Test hook: raw ranking values of the tensor-core path, shape (padded nq, padded n)."""
+        q, qd = self._query_array(queries)
+        nq = q.shape[0]
+        rows = ((nq + 127) // 128) * 128
+        cols = ((self.local_n + 255) // 256) * 256
+        out = np.empty((rows, cols), dtype=np.float32)
+        r, c = _U32(), _U32()
+        _check(_lib.mvf_gpu_tc_dump(self._h, q.ctypes.data_as(_P), int(qd), nq, k, -1 if metric is None else int(metric),
+                                    out.ctypes.data_as(_P), out.size, _c.byref(r), _c.byref(c)))
+        assert (r.value, c.value) == (rows, cols)
+        return out
 
     def search_raw(self, q_ptr, qdtype, nq, k, metric, ids_ptr, scores_ptr, iscores_ptr=None):
         """Host-pointer search without any numpy work (bench e2e loop)."""

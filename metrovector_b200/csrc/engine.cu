@@ -284,18 +284,27 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
     if (multi) { g->packed_local.reserve((size_t)nq * kk * 8); packed_local = (u64*)g->packed_local.p; }
 
     bool done = false;
+    bool tc_keys = false;
+    const float* tc_qconst = nullptr;
     if (mvf::tc::eligible(g->tc, g->path, s->dtype, qdtype, metric, nq, kk, s->local_n, s->d, s->pitch)) {
         mvf::tc::SearchArgs a;
         a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
-        a.dtype = s->dtype; a.metric = metric; a.queries = d_queries; a.nq = nq; a.k = kk;
-        a.id_add = (uint32_t)s->row_base;
-        a.out_packed = packed_local; a.out_ids = multi ? nullptr : d_ids; a.out_scores = multi ? nullptr : d_scores;
-        a.out_iscores = multi ? nullptr : d_iscores;
-        ScanTimer t(g);
-        uint64_t launches = 0;
-        mvf::tc::search(g->tc, a, g->stream, g->sm_count, &launches);
-        g->scan_launches++; g->all_launches += launches;
+        a.dtype = s->dtype; a.metric = metric; a.queries = d_queries; a.nq = nq; a.k = kk; a.dump = false;
+        mvf::tc::SearchResult r;
+        {
+            ScanTimer t(g);
+            r = mvf::tc::run(g->tc, a, g->stream, g->sm_count);
+        }
+        g->scan_launches++; g->all_launches += r.launches;
         g->last_path = 2;
+        // merge the per-item lists; keys are K2 ranking values, decoded with the per-query constant
+        k::MergeParams mp;
+        mp.in = r.lists; mp.q_stride = (size_t)r.chunks * kk; mp.list_stride = kk; mp.nlists = r.chunks; mp.k = kk;
+        mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 1; mp.qconst = r.qconst;
+        mp.out_packed = multi ? packed_local : nullptr;
+        mp.out_ids = multi ? nullptr : d_ids; mp.out_scores = multi ? nullptr : d_scores; mp.out_iscores = multi ? nullptr : d_iscores;
+        launch_merge(g, mp, nq);
+        tc_keys = true; tc_qconst = r.qconst;
         done = true;
     }
     if (!done) {
@@ -319,7 +328,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
             if (s->local_n > 0) launch_scan(g, s, p, NQ, &grid);
             k::MergeParams mp;
             mp.in = (const u64*)g->cand.p; mp.q_stride = (size_t)grid * kk; mp.list_stride = kk; mp.nlists = grid; mp.k = kk;
-            mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype;
+            mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 0; mp.qconst = nullptr;
             const size_t o = (size_t)q0 * kk;
             mp.out_packed = multi ? packed_local + o : nullptr;
             mp.out_ids = multi ? nullptr : d_ids + o;
@@ -337,7 +346,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
         g->all_launches++;
         k::MergeParams mp;
         mp.in = (const u64*)g->gathered.p; mp.q_stride = kk; mp.list_stride = cnt; mp.nlists = (uint32_t)g->world; mp.k = kk;
-        mp.id_add = 0; mp.metric = metric; mp.dtype = s->dtype;
+        mp.id_add = 0; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = tc_keys ? 1 : 0; mp.qconst = tc_qconst;
         mp.out_packed = nullptr; mp.out_ids = d_ids; mp.out_scores = d_scores; mp.out_iscores = d_iscores;
         launch_merge(g, mp, nq);
     }
@@ -687,6 +696,30 @@ int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint3
         CUDA_CHECK(cudaMemcpyAsync(out_ids, g->out_ids.p, cnt * 8, cudaMemcpyDeviceToHost, g->stream));
         if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, g->out_scores.p, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
         if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, g->out_iscores.p, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    });
+}
+
+int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq, uint32_t k, int metric,
+                    float* out, uint64_t out_elems, uint32_t* out_rows, uint32_t* out_cols) {
+    return guard([&] {
+        mvf_gpu* g = s->g;
+        if (metric == MVF_METRIC_SPACE_DEFAULT) metric = s->metric;
+        if (!mvf::tc::eligible(g->tc, 2, s->dtype, query_dtype, metric, nq, k, s->local_n, s->d, s->pitch))
+            throw MvfError::build_error("this space/query/metric combination has no tensor-core path");
+        CUDA_CHECK(cudaSetDevice(g->device));
+        const size_t qbytes = (size_t)nq * s->d * element_size((DataType)query_dtype);
+        g->queries.reserve(std::max<size_t>(qbytes, 16));
+        CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
+        mvf::tc::SearchArgs a;
+        a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
+        a.dtype = s->dtype; a.metric = metric; a.queries = g->queries.p; a.nq = nq; a.k = k; a.dump = true;
+        mvf::tc::SearchResult r = mvf::tc::run(g->tc, a, g->stream, g->sm_count);
+        const uint32_t rows = ((nq + mvf::tc::BM - 1) / mvf::tc::BM) * mvf::tc::BM;
+        if (out_rows) *out_rows = rows;
+        if (out_cols) *out_cols = r.dump_cols;
+        if ((uint64_t)rows * r.dump_cols > out_elems) throw MvfError::build_error("dump buffer too small");
+        CUDA_CHECK(cudaMemcpyAsync(out, r.dump, (size_t)rows * r.dump_cols * 4, cudaMemcpyDeviceToHost, g->stream));
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
     });
 }

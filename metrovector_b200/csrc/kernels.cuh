@@ -149,6 +149,8 @@ struct MergeParams {
     float* out_scores;        // [nq][k] or null
     int* out_iscores;         // [nq][k] or null
     int metric, dtype;
+    int tc_mode;              // keys hold K2's ranking value (tc_kernels.cuh); decode with qconst
+    const float* qconst;      // per query: 1/|q| (cosine), |q|^2 (L2; int32 bits for integer spaces)
 };
 
 // decode one merged candidate into the caller's output arrays
@@ -162,12 +164,18 @@ __device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, ui
     const bool int_score = (p.dtype == DT_I8 || p.dtype == DT_U8) && p.metric != M_COS;
     if (int_score) {
         int s = (int)(key ^ 0x80000000u);
+        if (p.tc_mode && p.metric == M_L2) s += __float_as_int(p.qconst[q]);      // |q|^2 + (|x|^2 - 2 q.x)
         if (p.metric == M_IP) s = -s;
         if (p.out_iscores) p.out_iscores[o] = valid ? s : 0x7fffffff;
         if (p.out_scores) p.out_scores[o] = valid ? (float)s : __uint_as_float(0x7fc00000u);
     } else {
         float s = unordered_f32(key);
-        if (p.metric == M_IP) s = 0.0f - s;
+        if (p.tc_mode) {
+            const float c = p.qconst[q];
+            if (p.metric == M_COS) s = fmaf(s, c, 1.0f);                           // 1 - q.x / (|q||x|)
+            else if (p.metric == M_L2) s = __fsqrt_rn(fmaxf(c + s, 0.0f));          // sqrt(|q|^2 + |x|^2 - 2 q.x)
+            else s = 0.0f - s;
+        } else if (p.metric == M_IP) s = 0.0f - s;
         if (p.out_iscores) p.out_iscores[o] = 0;
         if (p.out_scores) p.out_scores[o] = valid ? s : __uint_as_float(0x7fc00000u);
     }

@@ -1,0 +1,393 @@
+// tc_kernels.cuh -- K2, the batched path: queries x database contraction on tcgen05 tensor cores
+// with the per-query top-k selection fused into the accumulator epilogue (sm_100a only).
+//
+// Shape of the work: S = Q (nq x d) . X^T (n x d), both operands K-major exactly as stored
+// (row-major queries, row-major resident rows), so no transposes.  One CTA tile = 128 queries x
+// 256 database rows; K is walked in 128-byte blocks (64 f16 / 128 int8).  Operands are staged by
+// TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 4-stage shared-memory ring, multiplied by
+// single-thread tcgen05.mma instructions (kind::f16 with f32 accumulation, kind::i8 with s32
+// accumulation) into TMEM, and the two 128x256 accumulators in TMEM are double buffered so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  The distance matrix never leaves TMEM /
+// registers: each epilogue thread owns one query (one TMEM lane), reads its 256 scores with
+// tcgen05.ld, turns them into the metric's ranking value and keeps only values that beat the
+// query's current k-th best (threshold in a register, rare appends to a per-query buffer, warp-
+// cooperative bitonic compaction when a buffer fills).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Replaces the same reference loop as K1 (examples/similarity_search.rs:147-169) for large batches.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace mvf {
+namespace tc {
+
+using k::u64;
+using k::kInf;
+
+constexpr int BM = 128;            // queries per tile (TMEM lanes)
+constexpr int BN = 256;            // database rows per tile (TMEM columns, MMA N)
+constexpr int BKB = 128;           // K block in bytes (one 128-byte swizzle row)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BKB;  // 16 KiB
+constexpr int B_BYTES = BN * BKB;  // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int MAX_CAP = 512;       // candidate buffer entries per query (power of two)
+
+struct TcParams {
+    const float* norm;             // sqrt(sum x^2) per resident row
+    const float* sq;               // sum x^2 per row (f32, or int32 bits for integer spaces)
+    u64* cand;                     // [gridDim.x][BM][cap] scratch candidate buffers
+    u64* out_lists;                // [nq][chunks][k] sorted lists (key = ordered ranking value, id = local row)
+    float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
+    uint64_t n;                    // resident rows
+    uint32_t nq, k, cap;
+    uint32_t kblocks;              // ceil(d * elem / 128)
+    uint32_t mtiles, ntiles, chunks, tiles_per_chunk;
+    int metric;                    // k::M_L2 / M_IP / M_COS
+    int is_int;                    // 0: f16 operands / f32 accum, 1: int8 operands / s32 accum
+    uint32_t idesc;                // tcgen05 instruction descriptor
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <bool INT>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (INT) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 128 bytes, 8-row groups
+// 1024 bytes apart): start>>4 | LBO=1 | SBO=64 | version=1 | layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// warp-cooperative bitonic sort of P (power of two) words in shared memory
+__device__ __forceinline__ void warp_bitonic_sort(u64* a, int P, int lane) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (int i = lane; i < (P >> 1); i += 32) {
+                int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                int hi = lo | stride;
+                bool up = (lo & size) == 0;
+                u64 x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Compacts the candidate buffer of one query (owned by lane `owner` of this warp) to its k best,
+// sorted ascending; returns the new entry count and the k-th best word (kInf while fewer than k).
+__device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap, u64* scratch, int lane, int* new_cnt) {
+    int P = 32;
+    while (P < cnt) P <<= 1;
+    if (P > cap) P = cap;
+    for (int i = lane; i < P; i += 32) scratch[i] = i < cnt ? gbuf[i] : kInf;
+    warp_bitonic_sort(scratch, P, lane);
+    const int keep = cnt < k ? cnt : k;
+    for (int i = lane; i < keep; i += 32) gbuf[i] = scratch[i];
+    const u64 kth = (cnt >= k) ? scratch[k - 1] : kInf;
+    __syncwarp();
+    *new_cnt = keep;
+    return kth;
+}
+
+template <bool INT>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve shared memory: operand ring (1024-byte aligned) | sort scratch | column params | barriers
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    u64* scratch = reinterpret_cast<u64*>(ring + STAGES * STAGE_BYTES);           // [4 warps][cap]
+    float* prm = reinterpret_cast<float*>(scratch + 4 * p.cap);                   // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 2 * BN);                   // full[S] empty[S] tfull[2] tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t items = p.mtiles * p.chunks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
+                const uint32_t mt = w % p.mtiles, ch = w / p.mtiles;
+                const uint32_t t0 = ch * p.tiles_per_chunk;
+                const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+                for (uint32_t t = t0; t < t1; t++) {
+                    for (uint32_t kb = 0; kb < p.kblocks; kb++) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t a_dst = smem_u32(ring + stage * STAGE_BYTES);
+                        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+                        const int kc = (int)(kb * (INT ? 128u : 64u));   // element coordinate along K
+                        tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
+                        tma_load_2d(a_dst + A_BYTES, &map_x, full0 + 8 * stage, kc, (int)(t * BN));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
+                const uint32_t ch = w / p.mtiles;
+                const uint32_t t0 = ch * p.tiles_per_chunk;
+                const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+                for (uint32_t t = t0; t < t1; t++) {
+                    mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (uint32_t kb = 0; kb < p.kblocks; kb++) {
+                        mbar_wait(full0 + 8 * stage, phase);           // TMA bytes have landed
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(ring + stage * STAGE_BYTES);
+                        const uint64_t adesc = make_sdesc(a_addr), bdesc = make_sdesc(a_addr + A_BYTES);
+#pragma unroll
+                        for (uint32_t ks = 0; ks < 4; ks++)              // 4 x 32 bytes of K per 128-byte block
+                            umma<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                        umma_commit(empty0 + 8 * stage);                 // frees the smem slot when the MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(tfull0 + 8 * acc);                        // accumulator ready for the epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, one query per thread =====
+        const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31
+        const int qrow = quarter * 32 + lane;                           // query row inside the tile
+        const int etid = (warp - 2) * 32 + lane;                        // 0..127
+        u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
+        u64* mybuf = p.cand + ((size_t)blockIdx.x * BM + qrow) * p.cap;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
+            const uint32_t mt = w % p.mtiles, ch = w / p.mtiles;
+            const uint32_t t0 = ch * p.tiles_per_chunk;
+            const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+            int cnt = 0;
+            float thr_f = __int_as_float(0x7f800000);                   // +inf: everything passes until k are known
+            int thr_i = 0x7fffffff;
+            for (uint32_t t = t0; t < t1; t++) {
+                // per-column parameter of the ranking value for this tile (2 columns per thread)
+                float* pr = prm + acc * BN;
+                epi_bar_sync();                                          // previous tile's readers are done with pr
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int c = etid + h * EPI_THREADS;
+                    const uint64_t row = (uint64_t)t * BN + c;
+                    float v;
+                    if (row >= p.n) v = INT ? __int_as_float(0x7fffffff) : __int_as_float(0x7fc00000);   // never selected
+                    else if (INT) v = p.metric == k::M_L2 ? p.sq[row] : __int_as_float(0);
+                    else if (p.metric == k::M_L2) v = p.sq[row];
+                    else if (p.metric == k::M_COS) { const float nm = p.norm[row]; v = nm > 0.f ? -1.0f / nm : 0.0f; }
+                    else v = -1.0f;
+                    pr[c] = v;
+                }
+                epi_bar_sync();
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+                const bool full_tile = (uint64_t)(t + 1) * BN <= p.n;
+                for (int cc = 0; cc < BN / 32; cc++) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cc * 32, v);
+                    tmem_wait_ld();
+                    const uint32_t id0 = t * BN + cc * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float pj = pr[cc * 32 + j];
+                        if (INT) {
+                            const int a = (int)v[j];
+                            const int xx = __float_as_int(pj);
+                            const int s = p.metric == k::M_L2 ? xx - 2 * a : -a;
+                            if (p.dump) p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = (float)s;
+                            if (s <= thr_i && (full_tile || (uint64_t)id0 + j < p.n)) {
+                                mybuf[cnt++] = ((u64)k::ordered_i32(s) << 32) | (id0 + j);
+                            }
+                        } else {
+                            const float a = __uint_as_float(v[j]);
+                            const float s = p.metric == k::M_L2 ? fmaf(a, -2.0f, pj) : a * pj;
+                            if (p.dump) p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = s;
+                            if (s <= thr_f) mybuf[cnt++] = ((u64)k::ordered_f32(s) << 32) | (id0 + j);
+                        }
+                    }
+                    // a buffer that could overflow during the next 32 columns is compacted now, by the whole warp
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > (int)p.cap - 32);
+                    while (need) {
+                        const int owner = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
+                        u64* obuf = p.cand + ((size_t)blockIdx.x * BM + quarter * 32 + owner) * p.cap;
+                        __syncwarp();
+                        int ncnt;
+                        const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
+                        if (lane == owner) {
+                            cnt = ncnt;
+                            if (kth != kInf) {
+                                if (INT) thr_i = (int)((uint32_t)(kth >> 32) ^ 0x80000000u);
+                                else thr_f = k::unordered_f32((uint32_t)(kth >> 32));
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // 4 warps -> accumulator free
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            // end of the work item: every query's buffer becomes a sorted list of its k best
+            for (int owner = 0; owner < 32; owner++) {
+                const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
+                u64* obuf = p.cand + ((size_t)blockIdx.x * BM + quarter * 32 + owner) * p.cap;
+                __syncwarp();
+                int ncnt;
+                compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
+                const uint32_t q = mt * BM + quarter * 32 + owner;
+                if (q < p.nq) {
+                    u64* dst = p.out_lists + ((size_t)q * p.chunks + ch) * p.k;
+                    for (int i = lane; i < (int)p.k; i += 32) dst[i] = i < ncnt ? wscratch[i] : kInf;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// query preparation: copy the batch into a 16-byte-pitched operand buffer and compute the
+// per-query constant of the final score (cosine: 1/|q|; L2: |q|^2; integer L2: sum q^2 as int bits)
+template <bool INT, bool SIGNED>
+__global__ void __launch_bounds__(128) prep_queries(const void* q, unsigned char* out, uint32_t nq, uint32_t d, uint32_t pitch,
+                                                    float* qconst, int metric) {
+    const uint32_t qi = blockIdx.x;
+    if (qi >= nq) return;
+    const uint32_t es = INT ? 1 : 2;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(q) + (size_t)qi * d * es;
+    unsigned char* dst = out + (size_t)qi * pitch;
+    float fs = 0.f; int is = 0;
+    for (uint32_t j = threadIdx.x; j < pitch / es; j += blockDim.x) {
+        if (INT) {
+            unsigned char b = j < d ? src[j] : 0;
+            dst[j] = b;
+            int v = SIGNED ? (int)(signed char)b : (int)b;
+            is += v * v;
+        } else {
+            __half h = j < d ? reinterpret_cast<const __half*>(src)[j] : __float2half(0.f);
+            reinterpret_cast<__half*>(dst)[j] = h;
+            float v = __half2float(h);
+            fs = fmaf(v, v, fs);
+        }
+    }
+    __shared__ float rf[4]; __shared__ int ri[4];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { fs += __shfl_xor_sync(0xffffffffu, fs, off); is += __shfl_xor_sync(0xffffffffu, is, off); }
+    if ((threadIdx.x & 31) == 0) { rf[threadIdx.x >> 5] = fs; ri[threadIdx.x >> 5] = is; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float f = rf[0] + rf[1] + rf[2] + rf[3]; int i = ri[0] + ri[1] + ri[2] + ri[3];
+        float c;
+        if (INT) c = metric == k::M_L2 ? __int_as_float(i) : 0.f;
+        else if (metric == k::M_COS) { float nm = sqrtf(f); c = nm > 0.f ? 1.0f / nm : 0.0f; }
+        else c = f;
+        qconst[qi] = c;
+    }
+}
+
+}  // namespace tc
+}  // namespace mvf

@@ -1,37 +1,171 @@
-// tc_path.cuh -- tensor-core (tcgen05) batched path, K2.  Host-side state + entry points used by
-// engine.cu.  See tc_kernels.cuh for the kernels.
+// tc_path.cuh -- host side of K2 (tc_kernels.cuh): TMA tensor maps, work partitioning, launch.
+// Included by engine.cu only.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
+#include "mvf_host.hpp"
+#include "tc_kernels.cuh"
 
 namespace mvf {
 namespace tc {
 
+#define TC_CUDA_CHECK(expr)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            throw MvfError::cuda(std::string(cudaGetErrorName(_e)) + ": " + cudaGetErrorString(_e) + " at " #expr); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Buf {
+    void* p = nullptr; size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        TC_CUDA_CHECK(cudaMalloc(&p, n));
+        cap = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 struct TcState {
-    void* scratch = nullptr;      // candidate append buffers
-    size_t scratch_bytes = 0;
-    void* qprep = nullptr;        // prepared queries (operand layout) + per-query constants
-    size_t qprep_bytes = 0;
-    bool enabled = false;         // flipped on once the kernels are validated on hardware
+    EncodeTiledFn encode = nullptr;
+    Buf qprep, qconst, cand, lists, dump;
+    int min_batch = 64;            // auto path: batches at least this large go to the tensor cores (MVF_TC_MIN_BATCH)
+    bool attr_set = false;
 };
 
 struct SearchArgs {
     const unsigned char* rows; const float* norm; const float* sq;
     uint64_t n; uint32_t d, pitch; int dtype, metric;
-    const void* queries; uint32_t nq, k; uint32_t id_add;
-    unsigned long long* out_packed; uint64_t* out_ids; float* out_scores; int32_t* out_iscores;
+    const void* queries; uint32_t nq, k;
+    bool dump;                     // tests: also write the raw ranking values
+};
+struct SearchResult {
+    const u64* lists; uint32_t chunks; const float* qconst; const float* dump; uint32_t dump_cols; uint64_t launches;
 };
 
+inline void init(TcState& st) {
+    if (st.encode) return;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { cudaGetLastError(); throw MvfError::cuda("cuTensorMapEncodeTiled is not available from the driver"); }
+    st.encode = (EncodeTiledFn)fn;
+    if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch = std::max(1, std::atoi(c));
+}
+
+inline size_t smem_bytes(uint32_t cap) {
+    return 1024 + (size_t)STAGES * STAGE_BYTES + 4 * (size_t)cap * 8 + 2 * BN * 4 + (2 * STAGES + 4) * 8 + 16;
+}
+inline uint32_t cap_for_k(uint32_t k) { return k <= 16 ? 128u : k <= 64 ? 256u : 512u; }
+
+// K2 takes f16 spaces with f16 queries and int8/uint8 spaces (any metric except integer cosine,
+// whose exact definition needs a division per element), k <= 128, rows of at least one K block.
 inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int metric, uint32_t nq, uint32_t k, uint64_t n,
                      uint32_t d, uint32_t pitch) {
-    (void)path; (void)dtype; (void)qdtype; (void)metric; (void)nq; (void)k; (void)n; (void)d; (void)pitch;
-    return st.enabled && false;
+    (void)pitch;
+    if (path == 1) return false;
+    const bool f16 = dtype == k::DT_F16 && qdtype == k::DT_F16;
+    const bool i8 = (dtype == k::DT_I8 || dtype == k::DT_U8) && qdtype == dtype && metric != k::M_COS;
+    if (!(f16 || i8)) return false;
+    if (k > 128 || n == 0 || d == 0) return false;
+    if (path == 2) return true;
+    return nq >= (uint32_t)st.min_batch && n >= 4096;
 }
-inline void search(TcState&, const SearchArgs&, cudaStream_t, int, uint64_t*) {}
+
+inline void make_map(TcState& st, CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint32_t d, uint64_t pitch,
+                     uint32_t box_rows) {
+    const bool i8 = dtype != k::DT_F16;
+    cuuint64_t gdim[2] = {d, rows};
+    cuuint64_t gstride[1] = {pitch};
+    cuuint32_t box[2] = {i8 ? 128u : 64u, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = st.encode(map, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base),
+                           gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw MvfError::cuda("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+
+inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_count) {
+    init(st);
+    const bool is_int = a.dtype != k::DT_F16;
+    const uint32_t es = is_int ? 1 : 2;
+    const uint32_t qpitch = (a.d * es + 15u) & ~15u;
+    const uint32_t mtiles = (a.nq + BM - 1) / BM;
+    const uint32_t ntiles = (uint32_t)((a.n + BN - 1) / BN);
+    // work items = (query tile, contiguous run of database tiles); ~8 items per SM, each item keeps
+    // its own running thresholds, the item lists are merged afterwards
+    uint32_t chunks = std::max<uint32_t>(1, (8u * (uint32_t)sm_count + mtiles - 1) / mtiles);
+    chunks = std::min(chunks, ntiles);
+    const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+    chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    const uint32_t items = mtiles * chunks;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count, items);
+    const uint32_t cap = cap_for_k(a.k);
+
+    st.qprep.reserve((size_t)mtiles * BM * qpitch);
+    st.qconst.reserve((size_t)a.nq * 4);
+    st.cand.reserve((size_t)grid * BM * cap * 8);
+    st.lists.reserve((size_t)a.nq * chunks * a.k * 8);
+    uint64_t launches = 0;
+    TC_CUDA_CHECK(cudaMemsetAsync(st.qprep.p, 0, (size_t)mtiles * BM * qpitch, stream));
+    if (is_int) {
+        if (a.dtype == k::DT_I8)
+            prep_queries<true, true><<<a.nq, 128, 0, stream>>>(a.queries, (unsigned char*)st.qprep.p, a.nq, a.d, qpitch, (float*)st.qconst.p, a.metric);
+        else
+            prep_queries<true, false><<<a.nq, 128, 0, stream>>>(a.queries, (unsigned char*)st.qprep.p, a.nq, a.d, qpitch, (float*)st.qconst.p, a.metric);
+    } else {
+        prep_queries<false, false><<<a.nq, 128, 0, stream>>>(a.queries, (unsigned char*)st.qprep.p, a.nq, a.d, qpitch, (float*)st.qconst.p, a.metric);
+    }
+    TC_CUDA_CHECK(cudaGetLastError());
+    launches++;
+
+    CUtensorMap map_q, map_x;
+    make_map(st, &map_q, st.qprep.p, a.dtype, (uint64_t)mtiles * BM, a.d, qpitch, BM);
+    make_map(st, &map_x, a.rows, a.dtype, a.n, a.d, a.pitch, BN);
+
+    TcParams p;
+    p.norm = a.norm; p.sq = a.sq; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
+    p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
+    p.kblocks = (a.d * es + BKB - 1) / BKB;
+    p.mtiles = mtiles; p.ntiles = ntiles; p.chunks = chunks; p.tiles_per_chunk = tiles_per_chunk;
+    p.metric = a.metric; p.is_int = is_int ? 1 : 0;
+    const uint32_t fmt = a.dtype == k::DT_I8 ? 1u : 0u;     // kind::i8: 0 = unsigned, 1 = signed; kind::f16: 0 = F16
+    const uint32_t cfmt = is_int ? 2u : 1u;                  // accumulator: S32 / F32
+    p.idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (a.dump) {
+        st.dump.reserve((size_t)mtiles * BM * (size_t)ntiles * BN * 4);
+        p.dump = (float*)st.dump.p;
+    }
+    const size_t smem = smem_bytes(MAX_CAP);
+    if (!st.attr_set) {
+        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        st.attr_set = true;
+    }
+    if (is_int) gemm_topk_tc<true><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+    else gemm_topk_tc<false><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+    TC_CUDA_CHECK(cudaGetLastError());
+    launches++;
+    SearchResult r;
+    r.lists = (const u64*)st.lists.p; r.chunks = chunks; r.qconst = (const float*)st.qconst.p;
+    r.dump = (const float*)st.dump.p; r.dump_cols = ntiles * BN; r.launches = launches;
+    return r;
+}
+
 inline void release(TcState& st) {
-    if (st.scratch) cudaFree(st.scratch);
-    if (st.qprep) cudaFree(st.qprep);
-    st = TcState();
+    st.qprep.release(); st.qconst.release(); st.cand.release(); st.lists.release(); st.dump.release();
 }
 
 }  // namespace tc

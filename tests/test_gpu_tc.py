@@ -1,0 +1,80 @@
+"""K2, the tcgen05 tensor-core path, against the CPU oracle (and numpy for the raw contraction)."""
+import numpy as np
+import pytest
+
+import metrovector_b200 as mv
+import oracle
+from util import check_batch
+
+pytestmark = pytest.mark.gpu
+DT = {oracle.F16: mv.DataType.Float16, oracle.I8: mv.DataType.Int8, oracle.U8: mv.DataType.UInt8}
+
+
+def _rank_values(db, q, dtype, metric):
+    a = db.astype(np.float64)
+    b = q.astype(np.float64)
+    dot = b @ a.T
+    if metric == oracle.L2:
+        return (a * a).sum(1)[None, :] - 2 * dot
+    if metric == oracle.IP:
+        return -dot
+    nrm = np.sqrt((a * a).sum(1))
+    inv = np.where(nrm > 0, 1.0 / np.maximum(nrm, 1e-30), 0.0)
+    return -dot * inv[None, :]
+
+
+@pytest.mark.parametrize("dtype,d", [(oracle.F16, 64), (oracle.F16, 768), (oracle.F16, 200), (oracle.U8, 128), (oracle.I8, 96),
+                                     (oracle.U8, 300)])
+def test_raw_contraction_matches_numpy(engine, dtype, d):
+    n, nq = 700, 130                       # 3 database tiles (last one partial), 2 query tiles (last one partial)
+    db = mv.synth_fill_host(dtype, 31, 0, n, d)
+    q = mv.synth_fill_host(dtype, 32, 0, nq, d)
+    gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+    metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)
+    for metric in metrics:
+        got = gs.tc_dump(q, k=10, metric=metric)[:nq, :n]
+        want = _rank_values(db, q, dtype, metric)
+        if dtype == oracle.F16:
+            scale = np.abs(want).max()
+            assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * scale), (metric, np.abs(got - want).max())
+        else:
+            assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), metric
+    gs.free()
+
+
+@pytest.mark.parametrize("dtype,d,n", [(oracle.F16, 128, 20000), (oracle.F16, 768, 9000), (oracle.U8, 128, 30000),
+                                       (oracle.I8, 64, 12345), (oracle.F16, 72, 5000)])
+def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
+    db = mv.synth_fill_host(dtype, 41, 0, n, d)
+    gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+    engine.set_path(2)
+    try:
+        metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)
+        for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33)):
+            q = mv.synth_fill_host(dtype, 42, 0, nq, d)
+            q[0] = db[n // 2]
+            for metric in metrics:
+                ids, sc, isc = gs.search(q, k, metric=metric)
+                assert engine.profile_read()["last_path"] == 2
+                qq = q.astype(np.float32) if dtype == oracle.F16 else q
+                check_batch(db, dtype, metric, qq[:16], k, ids[:16], sc[:16], isc[:16])
+                check_batch(db, dtype, metric, qq[-3:], k, ids[-3:], sc[-3:], isc[-3:])
+    finally:
+        engine.set_path(0)
+        gs.free()
+
+
+def test_tensor_and_scan_paths_agree(engine):
+    n, d, nq, k = 50000, 256, 96, 10
+    db = mv.synth_fill_host(oracle.U8, 51, 0, n, d)
+    q = mv.synth_fill_host(oracle.U8, 52, 0, nq, d)
+    gs = engine.from_host(db, mv.DataType.UInt8, mv.DistanceMetric.L2)
+    try:
+        engine.set_path(1)
+        a = gs.search(q, k)
+        engine.set_path(2)
+        b = gs.search(q, k)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])      # integers: bit-identical
+    finally:
+        engine.set_path(0)
+        gs.free()
