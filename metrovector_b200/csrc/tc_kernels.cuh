@@ -47,6 +47,7 @@ struct TcParams {
     u64* cand;                     // [gridDim.x][BM][cap] scratch candidate buffers
     u64* out_lists;                // [nq][chunks][k] sorted lists (key = ordered ranking value, id = local row)
     float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
+    uint32_t* gthr;                // [mtiles*BM] tightest k-th-best key any CTA has seen per query (atomicMin)
     uint64_t n;                    // resident rows
     uint32_t nq, k, cap;
     uint32_t kblocks;              // ceil(d * elem / 128)
@@ -166,12 +167,15 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
     return kth;
 }
 
-template <bool INT>
+// MODE selects the ranking value computed from the accumulator `a` and the per-column parameter:
+//   MODE 0  (L2)            s = prm - 2a        prm = |x|^2           (float: fma; int: exact)
+//   MODE 1  (cosine / dot)  s = a * prm         prm = -1/|x| or -1    (float)   |  s = -a (int dot)
+template <bool INT, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve shared memory: operand ring (1024-byte aligned) | sort scratch | column params | barriers
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem;
     u64* scratch = reinterpret_cast<u64*>(ring + STAGES * STAGE_BYTES);           // [4 warps][cap]
     float* prm = reinterpret_cast<float*>(scratch + 4 * p.cap);                   // [2][BN]
@@ -253,56 +257,87 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         const int etid = (warp - 2) * 32 + lane;                        // 0..127
         u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
         u64* mybuf = p.cand + ((size_t)blockIdx.x * BM + qrow) * p.cap;
+        // this tile's per-column parameter, loaded one tile ahead (2 columns per thread)
+        auto load_param = [&](uint32_t t, int h) -> float {
+            const uint64_t row = (uint64_t)t * BN + etid + h * EPI_THREADS;
+            if (row >= p.n) return INT ? __int_as_float(0) : __int_as_float(0x7fc00000);
+            if (MODE == 0) return p.sq[row];                              // |x|^2 (int32 bits for integer spaces)
+            if (INT) return __int_as_float(0);
+            if (p.metric == k::M_COS) { const float nm = p.norm[row]; return nm > 0.f ? -1.0f / nm : 0.0f; }
+            return -1.0f;
+        };
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
             const uint32_t mt = w % p.mtiles, ch = w / p.mtiles;
             const uint32_t t0 = ch * p.tiles_per_chunk;
             const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+            const uint32_t q = mt * BM + qrow;
             int cnt = 0;
+            uint32_t thr_key = 0xffffffffu;                              // ordered key of the threshold
             float thr_f = __int_as_float(0x7f800000);                   // +inf: everything passes until k are known
             int thr_i = 0x7fffffff;
-            for (uint32_t t = t0; t < t1; t++) {
-                // per-column parameter of the ranking value for this tile (2 columns per thread)
+            {
                 float* pr = prm + acc * BN;
-                epi_bar_sync();                                          // previous tile's readers are done with pr
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int c = etid + h * EPI_THREADS;
-                    const uint64_t row = (uint64_t)t * BN + c;
-                    float v;
-                    if (row >= p.n) v = INT ? __int_as_float(0x7fffffff) : __int_as_float(0x7fc00000);   // never selected
-                    else if (INT) v = p.metric == k::M_L2 ? p.sq[row] : __int_as_float(0);
-                    else if (p.metric == k::M_L2) v = p.sq[row];
-                    else if (p.metric == k::M_COS) { const float nm = p.norm[row]; v = nm > 0.f ? -1.0f / nm : 0.0f; }
-                    else v = -1.0f;
-                    pr[c] = v;
-                }
+                pr[etid] = load_param(t0, 0);
+                pr[etid + EPI_THREADS] = load_param(t0, 1);
                 epi_bar_sync();
+            }
+            for (uint32_t t = t0; t < t1; t++) {
+                const float* pr = prm + acc * BN;
+                float nx0 = 0.f, nx1 = 0.f;
+                if (t + 1 < t1) { nx0 = load_param(t + 1, 0); nx1 = load_param(t + 1, 1); }
+                // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen
+                const uint32_t gk = __ldcg(p.gthr + q);   // L2, never a stale L1 line
+                if (gk < thr_key) {
+                    thr_key = gk;
+                    if (INT) thr_i = (int)(gk ^ 0x80000000u); else thr_f = k::unordered_f32(gk);
+                }
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-                const bool full_tile = (uint64_t)(t + 1) * BN <= p.n;
+                const int64_t left0 = (int64_t)p.n - (int64_t)t * BN;  // valid columns from the tile start
                 for (int cc = 0; cc < BN / 32; cc++) {
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
                     tmem_wait_ld();
                     const uint32_t id0 = t * BN + cc * 32;
+                    const float4* pr4 = reinterpret_cast<const float4*>(pr + cc * 32);
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float pj = pr[cc * 32 + j];
-                        if (INT) {
-                            const int a = (int)v[j];
-                            const int xx = __float_as_int(pj);
-                            const int s = p.metric == k::M_L2 ? xx - 2 * a : -a;
-                            if (p.dump) p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = (float)s;
-                            if (s <= thr_i && (full_tile || (uint64_t)id0 + j < p.n)) {
-                                mybuf[cnt++] = ((u64)k::ordered_i32(s) << 32) | (id0 + j);
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        const float4 pq = pr4[j4];
+                        const float pj[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int j = j4 * 4 + e;
+                            if (INT) {
+                                const int a = (int)v[j];
+                                const int s = MODE == 0 ? __float_as_int(pj[e]) - 2 * a : -a;
+                                v[j] = (uint32_t)s;
+                                if (s <= thr_i) mask |= 1u << j;
+                            } else {
+                                const float a = __uint_as_float(v[j]);
+                                const float s = MODE == 0 ? fmaf(a, -2.0f, pj[e]) : a * pj[e];
+                                v[j] = __float_as_uint(s);
+                                if (s <= thr_f) mask |= 1u << j;
                             }
-                        } else {
-                            const float a = __uint_as_float(v[j]);
-                            const float s = p.metric == k::M_L2 ? fmaf(a, -2.0f, pj) : a * pj;
-                            if (p.dump) p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = s;
-                            if (s <= thr_f) mybuf[cnt++] = ((u64)k::ordered_f32(s) << 32) | (id0 + j);
+                        }
+                    }
+                    const int64_t left = left0 - cc * 32;               // columns of this 32-group inside the database
+                    if (left < 32) mask &= left <= 0 ? 0u : ((1u << (int)left) - 1u);
+                    if (p.dump) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] =
+                                INT ? (float)(int)v[j] : __uint_as_float(v[j]);
+                    }
+                    if (mask) {                                          // rare per thread
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if (mask & (1u << j)) {
+                                const uint32_t key = INT ? k::ordered_i32((int)v[j]) : k::ordered_f32(__uint_as_float(v[j]));
+                                mybuf[cnt++] = ((u64)key << 32) | (id0 + j);
+                            }
                         }
                     }
                     // a buffer that could overflow during the next 32 columns is compacted now, by the whole warp
@@ -318,8 +353,12 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         if (lane == owner) {
                             cnt = ncnt;
                             if (kth != kInf) {
-                                if (INT) thr_i = (int)((uint32_t)(kth >> 32) ^ 0x80000000u);
-                                else thr_f = k::unordered_f32((uint32_t)(kth >> 32));
+                                const uint32_t kk = (uint32_t)(kth >> 32);
+                                if (kk < thr_key) {
+                                    thr_key = kk;
+                                    if (INT) thr_i = (int)(kk ^ 0x80000000u); else thr_f = k::unordered_f32(kk);
+                                }
+                                atomicMin(p.gthr + q, kk);
                             }
                         }
                     }
@@ -328,6 +367,11 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // 4 warps -> accumulator free
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (t + 1 < t1) {                                          // publish the next tile's parameters
+                    float* prn = prm + acc * BN;
+                    prn[etid] = nx0; prn[etid + EPI_THREADS] = nx1;
+                }
+                epi_bar_sync();
             }
             // end of the work item: every query's buffer becomes a sorted list of its k best
             for (int owner = 0; owner < 32; owner++) {
@@ -335,10 +379,11 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 u64* obuf = p.cand + ((size_t)blockIdx.x * BM + quarter * 32 + owner) * p.cap;
                 __syncwarp();
                 int ncnt;
-                compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
-                const uint32_t q = mt * BM + quarter * 32 + owner;
-                if (q < p.nq) {
-                    u64* dst = p.out_lists + ((size_t)q * p.chunks + ch) * p.k;
+                const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
+                const uint32_t qo = mt * BM + quarter * 32 + owner;
+                if (lane == 0 && kth != kInf) atomicMin(p.gthr + qo, (uint32_t)(kth >> 32));
+                if (qo < p.nq) {
+                    u64* dst = p.out_lists + ((size_t)qo * p.chunks + ch) * p.k;
                     for (int i = lane; i < (int)p.k; i += 32) dst[i] = i < ncnt ? wscratch[i] : kInf;
                 }
                 __syncwarp();

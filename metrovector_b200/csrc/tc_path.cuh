@@ -40,7 +40,7 @@ struct Buf {
 
 struct TcState {
     EncodeTiledFn encode = nullptr;
-    Buf qprep, qconst, cand, lists, dump;
+    Buf qprep, qconst, cand, lists, dump, gthr;
     int min_batch = 64;            // auto path: batches at least this large go to the tensor cores (MVF_TC_MIN_BATCH)
     bool attr_set = false;
 };
@@ -118,6 +118,8 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     st.qconst.reserve((size_t)a.nq * 4);
     st.cand.reserve((size_t)grid * BM * cap * 8);
     st.lists.reserve((size_t)a.nq * chunks * a.k * 8);
+    st.gthr.reserve((size_t)mtiles * BM * 4);
+    TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mtiles * BM * 4, stream));
     uint64_t launches = 0;
     TC_CUDA_CHECK(cudaMemsetAsync(st.qprep.p, 0, (size_t)mtiles * BM * qpitch, stream));
     if (is_int) {
@@ -137,6 +139,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
 
     TcParams p;
     p.norm = a.norm; p.sq = a.sq; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
+    p.gthr = (uint32_t*)st.gthr.p;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
     p.kblocks = (a.d * es + BKB - 1) / BKB;
     p.mtiles = mtiles; p.ntiles = ntiles; p.chunks = chunks; p.tiles_per_chunk = tiles_per_chunk;
@@ -150,12 +153,20 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     }
     const size_t smem = smem_bytes(MAX_CAP);
     if (!st.attr_set) {
-        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         st.attr_set = true;
     }
-    if (is_int) gemm_topk_tc<true><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
-    else gemm_topk_tc<false><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+    const bool l2 = a.metric == k::M_L2;
+    if (is_int) {
+        if (l2) gemm_topk_tc<true, 0><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+        else gemm_topk_tc<true, 1><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+    } else {
+        if (l2) gemm_topk_tc<false, 0><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+        else gemm_topk_tc<false, 1><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
+    }
     TC_CUDA_CHECK(cudaGetLastError());
     launches++;
     SearchResult r;
@@ -165,7 +176,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
 }
 
 inline void release(TcState& st) {
-    st.qprep.release(); st.qconst.release(); st.cand.release(); st.lists.release(); st.dump.release();
+    st.qprep.release(); st.qconst.release(); st.cand.release(); st.lists.release(); st.dump.release(); st.gthr.release();
 }
 
 }  // namespace tc
