@@ -20,6 +20,9 @@ the global merge when N>1).  Rank 0 prints ONE JSON line.
 
 Workloads are BASELINE.json's configs; the database is synthetic (counter-based generator, filled
 on the device), row-sharded over the ranks ("strong" scaling: the global database is fixed).
+Default workload: D = 100M x 768 f16 cosine top-10, batch 1 -- the configuration north_star's target
+is quoted on; its 153.6 GB fit one B200, so the same workload runs at every N.  `--workload B` is
+BASELINE.json configs[1] (1M x 768 f32 L2 top-10, batch 1).
 """
 import argparse
 import ctypes
@@ -157,7 +160,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MVF_BENCH_WORKLOAD", "B"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("MVF_BENCH_WORKLOAD", "D"), choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debug)")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 scan kernel, 2 tensor-core kernel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
