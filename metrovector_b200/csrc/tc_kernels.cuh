@@ -13,8 +13,8 @@
 // query's current k-th best (threshold in a register, rare appends to a per-query buffer, warp-
 // cooperative bitonic compaction when a buffer fills).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = two epilogue warpgroups (TMEM lane quarter = warp_id % 4, column half = group).
 // Replaces the same reference loop as K1 (examples/similarity_search.rs:147-169) for large batches.
 #pragma once
 #include <cuda.h>
@@ -33,21 +33,23 @@ using k::kInf;
 constexpr int BM = 128;            // queries per tile (TMEM lanes)
 constexpr int BN = 256;            // database rows per tile (TMEM columns, MMA N)
 constexpr int BKB = 128;           // K block in bytes (one 128-byte swizzle row)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * BKB;  // 16 KiB
 constexpr int B_BYTES = BN * BKB;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_GROUPS = 2;      // epilogue warpgroups: each takes BN / EPI_GROUPS columns of every tile
+constexpr int EPI_THREADS = 128 * EPI_GROUPS;
+constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int EPI_COLS = BN / EPI_GROUPS;
 constexpr int MAX_CAP = 512;       // candidate buffer entries per query (power of two)
 
 struct TcParams {
     const float* norm;             // sqrt(sum x^2) per resident row
     const float* sq;               // sum x^2 per row (f32, or int32 bits for integer spaces)
-    u64* cand;                     // [gridDim.x][BM][cap] scratch candidate buffers
-    u64* out_lists;                // [nq][chunks][k] sorted lists (key = ordered ranking value, id = local row)
+    u64* cand;                     // [gridDim.x][EPI_GROUPS][BM][cap] scratch candidate buffers
+    u64* out_lists;                // [nq][chunks*EPI_GROUPS][k] sorted lists (key = ordered ranking value, id = local row)
     float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
-    uint32_t* gthr;                // [mtiles*BM] tightest k-th-best key any CTA has seen per query (atomicMin)
+    uint32_t* gthr;                // [(mtiles rounded up to the cluster size)*BM] tightest k-th-best key any CTA has seen per query (atomicMin)
     uint64_t n;                    // resident rows
     uint32_t nq, k, cap;
     uint32_t kblocks;              // ceil(d * elem / 128)
@@ -84,6 +86,19 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -126,7 +141,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 128 bytes, 8-row groups
 // 1024 bytes apart): start>>4 | LBO=1 | SBO=64 | version=1 | layout SWIZZLE_128B
@@ -170,53 +185,67 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // MODE selects the ranking value computed from the accumulator `a` and the per-column parameter:
 //   MODE 0  (L2)            s = prm - 2a        prm = |x|^2           (float: fma; int: exact)
 //   MODE 1  (cosine / dot)  s = a * prm         prm = -1/|x| or -1    (float)   |  s = -a (int dot)
-template <bool INT, int MODE>
+// CL = 2: CTA pairs (thread-block clusters) work on the same database tiles for two different query
+// tiles; each CTA fetches half of the 256-row database tile and TMA-multicasts it into both CTAs'
+// shared memory, so L2 -> SM operand traffic per tile drops from 576 KB to 384 KB and the pair
+// stays in lockstep on the same rows.
+template <bool INT, int MODE, int STAGES, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve shared memory: operand ring (1024-byte aligned) | sort scratch | column params | barriers
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem;
-    u64* scratch = reinterpret_cast<u64*>(ring + STAGES * STAGE_BYTES);           // [4 warps][cap]
-    float* prm = reinterpret_cast<float*>(scratch + 4 * p.cap);                   // [2][BN]
+    u64* scratch = reinterpret_cast<u64*>(ring + STAGES * STAGE_BYTES);           // [epilogue warps][cap]
+    float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [2][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 2 * BN);                   // full[S] empty[S] tfull[2] tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
-    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * MAX_STAGES), tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_x);
-        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, EPI_THREADS / 32); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tcgen05_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                     // peers' barriers exist before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t items = p.mtiles * p.chunks;
+    // work items: (query-tile group of CL tiles, run of database tiles); the CTAs of a cluster take the
+    // same item and differ only in the query tile
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    const uint32_t mgroups = (p.mtiles + CL - 1) / CL;
+    const uint32_t items = mgroups * p.chunks;
+    const uint32_t w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
-                const uint32_t mt = w % p.mtiles, ch = w / p.mtiles;
+            for (uint32_t w = w_first; w < items; w += w_step) {
+                const uint32_t mt = (w % mgroups) * CL + crank, ch = w / mgroups;
                 const uint32_t t0 = ch * p.tiles_per_chunk;
                 const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
                 for (uint32_t t = t0; t < t1; t++) {
                     for (uint32_t kb = 0; kb < p.kblocks; kb++) {
-                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);          // every CTA of the cluster released the slot
                         const uint32_t a_dst = smem_u32(ring + stage * STAGE_BYTES);
                         mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
                         const int kc = (int)(kb * (INT ? 128u : 64u));   // element coordinate along K
                         tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
-                        tma_load_2d(a_dst + A_BYTES, &map_x, full0 + 8 * stage, kc, (int)(t * BN));
+                        if (CL > 1)      // this CTA's share of the database tile, delivered to every CTA of the cluster
+                            tma_load_2d_mc(a_dst + A_BYTES + crank * (B_BYTES / CL), &map_x, full0 + 8 * stage, kc,
+                                           (int)(t * BN + crank * (BN / CL)), (uint16_t)((1u << CL) - 1));
+                        else
+                            tma_load_2d(a_dst + A_BYTES, &map_x, full0 + 8 * stage, kc, (int)(t * BN));
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -226,8 +255,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
-                const uint32_t ch = w / p.mtiles;
+            for (uint32_t w = w_first; w < items; w += w_step) {
+                const uint32_t ch = w / mgroups;
                 const uint32_t t0 = ch * p.tiles_per_chunk;
                 const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
                 for (uint32_t t = t0; t < t1; t++) {
@@ -242,7 +271,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
                         for (uint32_t ks = 0; ks < 4; ks++)              // 4 x 32 bytes of K per 128-byte block
                             umma<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
-                        umma_commit(empty0 + 8 * stage);                 // frees the smem slot when the MMAs retire
+                        if (CL > 1) umma_commit_mc(empty0 + 8 * stage, (uint16_t)((1u << CL) - 1));   // slot free in every CTA
+                        else umma_commit(empty0 + 8 * stage);            // frees the smem slot when the MMAs retire
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(tfull0 + 8 * acc);                        // accumulator ready for the epilogue
@@ -251,15 +281,18 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue: 4 warps, one query per thread =====
+        // ===== epilogue: 2 warpgroups x 4 warps; a thread owns one query (TMEM lane) and the
+        // warpgroup's half of the tile's columns =====
         const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31
+        const int grp = (warp - 2) >> 2;                                // column half
         const int qrow = quarter * 32 + lane;                           // query row inside the tile
-        const int etid = (warp - 2) * 32 + lane;                        // 0..127
+        const int etid = (warp - 2) * 32 + lane;                        // 0..255 = the column this thread stages
         u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
-        u64* mybuf = p.cand + ((size_t)blockIdx.x * BM + qrow) * p.cap;
-        // this tile's per-column parameter, loaded one tile ahead (2 columns per thread)
-        auto load_param = [&](uint32_t t, int h) -> float {
-            const uint64_t row = (uint64_t)t * BN + etid + h * EPI_THREADS;
+        u64* const cta_cand = p.cand + ((size_t)blockIdx.x * EPI_GROUPS + grp) * BM * p.cap;
+        u64* mybuf = cta_cand + (size_t)qrow * p.cap;
+        // this tile's per-column parameter, loaded one tile ahead (1 column per thread)
+        auto load_param = [&](uint32_t t) -> float {
+            const uint64_t row = (uint64_t)t * BN + etid;
             if (row >= p.n) return INT ? __int_as_float(0) : __int_as_float(0x7fc00000);
             if (MODE == 0) return p.sq[row];                              // |x|^2 (int32 bits for integer spaces)
             if (INT) return __int_as_float(0);
@@ -267,8 +300,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             return -1.0f;
         };
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t w = blockIdx.x; w < items; w += gridDim.x) {
-            const uint32_t mt = w % p.mtiles, ch = w / p.mtiles;
+        for (uint32_t w = w_first; w < items; w += w_step) {
+            const uint32_t mt = (w % mgroups) * CL + crank, ch = w / mgroups;
             const uint32_t t0 = ch * p.tiles_per_chunk;
             const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
             const uint32_t q = mt * BM + qrow;
@@ -278,30 +311,31 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             int thr_i = 0x7fffffff;
             {
                 float* pr = prm + acc * BN;
-                pr[etid] = load_param(t0, 0);
-                pr[etid + EPI_THREADS] = load_param(t0, 1);
+                pr[etid] = load_param(t0);
+                const uint32_t g0 = __ldcg(p.gthr + q);
+                if (g0 < thr_key) {
+                    thr_key = g0;
+                    if (INT) thr_i = (int)(g0 ^ 0x80000000u); else thr_f = k::unordered_f32(g0);
+                }
                 epi_bar_sync();
             }
             for (uint32_t t = t0; t < t1; t++) {
                 const float* pr = prm + acc * BN;
-                float nx0 = 0.f, nx1 = 0.f;
-                if (t + 1 < t1) { nx0 = load_param(t + 1, 0); nx1 = load_param(t + 1, 1); }
-                // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen
-                const uint32_t gk = __ldcg(p.gthr + q);   // L2, never a stale L1 line
-                if (gk < thr_key) {
-                    thr_key = gk;
-                    if (INT) thr_i = (int)(gk ^ 0x80000000u); else thr_f = k::unordered_f32(gk);
-                }
+                float nx0 = 0.f;
+                if (t + 1 < t1) nx0 = load_param(t + 1);
+                // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen.
+                // The word is read from L2 now and applied after this tile, so its latency is hidden.
+                const uint32_t gk = __ldcg(p.gthr + q);
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-                const int64_t left0 = (int64_t)p.n - (int64_t)t * BN;  // valid columns from the tile start
-                for (int cc = 0; cc < BN / 32; cc++) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * EPI_COLS;
+                const int64_t left0 = (int64_t)p.n - (int64_t)t * BN - grp * EPI_COLS;  // valid columns from this half's start
+                for (int cc = 0; cc < EPI_COLS / 32; cc++) {
                     uint32_t v[32];
                     tmem_ld32(taddr + cc * 32, v);
                     tmem_wait_ld();
-                    const uint32_t id0 = t * BN + cc * 32;
-                    const float4* pr4 = reinterpret_cast<const float4*>(pr + cc * 32);
+                    const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
+                    const float4* pr4 = reinterpret_cast<const float4*>(pr + grp * EPI_COLS + cc * 32);
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; j4++) {
@@ -346,7 +380,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         const int owner = __ffs(need) - 1;
                         need &= need - 1;
                         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
-                        u64* obuf = p.cand + ((size_t)blockIdx.x * BM + quarter * 32 + owner) * p.cap;
+                        u64* obuf = cta_cand + (size_t)(quarter * 32 + owner) * p.cap;
                         __syncwarp();
                         int ncnt;
                         const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
@@ -365,25 +399,29 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // 4 warps -> accumulator free
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // all epilogue warps -> accumulator free
+                if (gk < thr_key) {
+                    thr_key = gk;
+                    if (INT) thr_i = (int)(gk ^ 0x80000000u); else thr_f = k::unordered_f32(gk);
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 if (t + 1 < t1) {                                          // publish the next tile's parameters
                     float* prn = prm + acc * BN;
-                    prn[etid] = nx0; prn[etid + EPI_THREADS] = nx1;
+                    prn[etid] = nx0;
                 }
                 epi_bar_sync();
             }
             // end of the work item: every query's buffer becomes a sorted list of its k best
             for (int owner = 0; owner < 32; owner++) {
                 const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
-                u64* obuf = p.cand + ((size_t)blockIdx.x * BM + quarter * 32 + owner) * p.cap;
+                u64* obuf = cta_cand + (size_t)(quarter * 32 + owner) * p.cap;
                 __syncwarp();
                 int ncnt;
                 const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
                 const uint32_t qo = mt * BM + quarter * 32 + owner;
                 if (lane == 0 && kth != kInf) atomicMin(p.gthr + qo, (uint32_t)(kth >> 32));
                 if (qo < p.nq) {
-                    u64* dst = p.out_lists + ((size_t)qo * p.chunks + ch) * p.k;
+                    u64* dst = p.out_lists + ((size_t)qo * (p.chunks * EPI_GROUPS) + ch * EPI_GROUPS + grp) * p.k;
                     for (int i = lane; i < (int)p.k; i += 32) dst[i] = i < ncnt ? wscratch[i] : kInf;
                 }
                 __syncwarp();
@@ -392,6 +430,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                     // no CTA leaves while a peer may still write into it
     if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 

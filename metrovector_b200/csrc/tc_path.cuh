@@ -41,6 +41,7 @@ struct Buf {
 struct TcState {
     EncodeTiledFn encode = nullptr;
     Buf qprep, qconst, cand, lists, dump, gthr;
+    int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
     int min_batch = 64;            // auto path: batches at least this large go to the tensor cores (MVF_TC_MIN_BATCH)
     bool attr_set = false;
 };
@@ -63,10 +64,13 @@ inline void init(TcState& st) {
     if (e != cudaSuccess || !fn) { cudaGetLastError(); throw MvfError::cuda("cuTensorMapEncodeTiled is not available from the driver"); }
     st.encode = (EncodeTiledFn)fn;
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch = std::max(1, std::atoi(c));
+    if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
 }
 
+inline int stages_for_cap(uint32_t cap) { return cap > 256 ? 3 : 4; }   // the sort scratch of k > 64 costs one operand stage
 inline size_t smem_bytes(uint32_t cap) {
-    return 1024 + (size_t)STAGES * STAGE_BYTES + 4 * (size_t)cap * 8 + 2 * BN * 4 + (2 * STAGES + 4) * 8 + 16;
+    return 1024 + (size_t)stages_for_cap(cap) * STAGE_BYTES + (EPI_THREADS / 32) * (size_t)cap * 8 + 2 * BN * 4 +
+           (2 * MAX_STAGES + 4) * 8 + 16;
 }
 inline uint32_t cap_for_k(uint32_t k) { return k <= 16 ? 128u : k <= 64 ? 256u : 512u; }
 
@@ -82,6 +86,16 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
     if (k > 128 || n == 0 || d == 0) return false;
     if (path == 2) return true;
     return nq >= (uint32_t)st.min_batch && n >= 4096;
+}
+
+template <bool INT, int MODE>
+inline const void* select_kernel_sc(int stages, int cl) {
+    if (stages == 3) return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 3, 2> : (const void*)gemm_topk_tc<INT, MODE, 3, 1>;
+    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 4, 2> : (const void*)gemm_topk_tc<INT, MODE, 4, 1>;
+}
+inline const void* select_kernel(bool is_int, bool l2, int stages, int cl) {
+    if (is_int) return l2 ? select_kernel_sc<true, 0>(stages, cl) : select_kernel_sc<true, 1>(stages, cl);
+    return l2 ? select_kernel_sc<false, 0>(stages, cl) : select_kernel_sc<false, 1>(stages, cl);
 }
 
 inline void make_map(TcState& st, CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint32_t d, uint64_t pitch,
@@ -110,16 +124,18 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     chunks = std::min(chunks, ntiles);
     const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
     chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
-    const uint32_t items = mtiles * chunks;
-    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count, items);
+    const uint32_t CL = (st.cluster == 2 && mtiles >= 2) ? 2u : 1u;
+    const uint32_t mgroups = (mtiles + CL - 1) / CL;
+    const uint32_t items = mgroups * chunks;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count / CL, items) * CL;
     const uint32_t cap = cap_for_k(a.k);
 
     st.qprep.reserve((size_t)mtiles * BM * qpitch);
     st.qconst.reserve((size_t)a.nq * 4);
-    st.cand.reserve((size_t)grid * BM * cap * 8);
-    st.lists.reserve((size_t)a.nq * chunks * a.k * 8);
-    st.gthr.reserve((size_t)mtiles * BM * 4);
-    TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mtiles * BM * 4, stream));
+    st.cand.reserve((size_t)grid * EPI_GROUPS * BM * cap * 8);
+    st.lists.reserve((size_t)a.nq * chunks * EPI_GROUPS * a.k * 8);
+    st.gthr.reserve((size_t)mgroups * CL * BM * 4);
+    TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mgroups * CL * BM * 4, stream));
     uint64_t launches = 0;
     TC_CUDA_CHECK(cudaMemsetAsync(st.qprep.p, 0, (size_t)mtiles * BM * qpitch, stream));
     if (is_int) {
@@ -135,7 +151,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
 
     CUtensorMap map_q, map_x;
     make_map(st, &map_q, st.qprep.p, a.dtype, (uint64_t)mtiles * BM, a.d, qpitch, BM);
-    make_map(st, &map_x, a.rows, a.dtype, a.n, a.d, a.pitch, BN);
+    make_map(st, &map_x, a.rows, a.dtype, a.n, a.d, a.pitch, BN / CL);
 
     TcParams p;
     p.norm = a.norm; p.sq = a.sq; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
@@ -151,26 +167,22 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
         st.dump.reserve((size_t)mtiles * BM * (size_t)ntiles * BN * 4);
         p.dump = (float*)st.dump.p;
     }
-    const size_t smem = smem_bytes(MAX_CAP);
-    if (!st.attr_set) {
-        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TC_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        st.attr_set = true;
-    }
     const bool l2 = a.metric == k::M_L2;
-    if (is_int) {
-        if (l2) gemm_topk_tc<true, 0><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
-        else gemm_topk_tc<true, 1><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
-    } else {
-        if (l2) gemm_topk_tc<false, 0><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
-        else gemm_topk_tc<false, 1><<<grid, THREADS, smem_bytes(cap), stream>>>(map_q, map_x, p);
-    }
+    const void* fn = select_kernel(is_int, l2, cap > 256 ? 3 : 4, (int)CL);
+    const size_t smem = smem_bytes(cap);
+    TC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&map_q, (void*)&map_x, (void*)&p};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TC_CUDA_CHECK(cudaLaunchKernelExC(&cfg, fn, args));
     TC_CUDA_CHECK(cudaGetLastError());
     launches++;
     SearchResult r;
-    r.lists = (const u64*)st.lists.p; r.chunks = chunks; r.qconst = (const float*)st.qconst.p;
+    r.lists = (const u64*)st.lists.p; r.chunks = chunks * EPI_GROUPS; r.qconst = (const float*)st.qconst.p;
     r.dump = (const float*)st.dump.p; r.dump_cols = ntiles * BN; r.launches = launches;
     return r;
 }
