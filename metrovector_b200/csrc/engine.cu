@@ -98,6 +98,7 @@ struct mvf_gpu {
     int ctas_per_sm_cap = 0;   // MVF_SCAN_CTAS_PER_SM, 0 = occupancy
     DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2];
     int merge_tmp_flip = 0;
+    unsigned char* pinned_out = nullptr;   // 64 KiB pinned mirror for small results
     std::map<std::pair<const void*, size_t>, int> occ_cache;
     mvf::tc::TcState tc;
 };
@@ -514,6 +515,7 @@ void mvf_gpu_shutdown(mvf_gpu* g) {
     g->cand.release(); g->packed_local.release(); g->gathered.release(); g->queries.release();
     g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release();
     mvf::tc::release(g->tc);
+    if (g->pinned_out) cudaFreeHost(g->pinned_out);
     if (g->own_stream) cudaStreamDestroy(g->stream);
     delete g;
 }
@@ -689,14 +691,29 @@ int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint3
         const size_t qbytes = (size_t)nq * s->d * element_size((DataType)query_dtype);
         const size_t cnt = (size_t)nq * k;
         g->queries.reserve(std::max<size_t>(qbytes, 16));
-        g->out_ids.reserve(cnt * 8); g->out_scores.reserve(cnt * 4); g->out_iscores.reserve(cnt * 4);
+        // results live in one device block [ids | scores | iscores]; small results come back in a single
+        // D2H copy through a pinned mirror (one driver call instead of three), large ones directly
+        g->out_ids.reserve(cnt * 16);
+        unsigned char* dev = (unsigned char*)g->out_ids.p;
+        uint64_t* d_ids = (uint64_t*)dev;
+        float* d_scores = (float*)(dev + cnt * 8);
+        int32_t* d_isc = (int32_t*)(dev + cnt * 12);
         CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
-        search_device(s, g->queries.p, query_dtype, nq, k, metric, (uint64_t*)g->out_ids.p, (float*)g->out_scores.p,
-                      out_iscores ? (int32_t*)g->out_iscores.p : nullptr);
-        CUDA_CHECK(cudaMemcpyAsync(out_ids, g->out_ids.p, cnt * 8, cudaMemcpyDeviceToHost, g->stream));
-        if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, g->out_scores.p, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
-        if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, g->out_iscores.p, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
-        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        search_device(s, g->queries.p, query_dtype, nq, k, metric, d_ids, d_scores, out_iscores ? d_isc : nullptr);
+        const size_t back = cnt * (out_iscores ? 16 : 12);
+        if (back <= 64 * 1024) {
+            if (!g->pinned_out) CUDA_CHECK(cudaMallocHost((void**)&g->pinned_out, 64 * 1024));
+            CUDA_CHECK(cudaMemcpyAsync(g->pinned_out, dev, back, cudaMemcpyDeviceToHost, g->stream));
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+            std::memcpy(out_ids, g->pinned_out, cnt * 8);
+            if (out_scores) std::memcpy(out_scores, g->pinned_out + cnt * 8, cnt * 4);
+            if (out_iscores) std::memcpy(out_iscores, g->pinned_out + cnt * 12, cnt * 4);
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids, cnt * 8, cudaMemcpyDeviceToHost, g->stream));
+            if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, d_scores, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
+            if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, d_isc, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        }
     });
 }
 

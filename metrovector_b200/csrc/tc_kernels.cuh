@@ -189,7 +189,7 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // tiles; each CTA fetches half of the 256-row database tile and TMA-multicasts it into both CTAs'
 // shared memory, so L2 -> SM operand traffic per tile drops from 576 KB to 384 KB and the pair
 // stays in lockstep on the same rows.
-template <bool INT, int MODE, int STAGES, int CL>
+template <bool INT, int MODE, int STAGES, int CL, int LDG>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -330,10 +330,16 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * EPI_COLS;
                 const int64_t left0 = (int64_t)p.n - (int64_t)t * BN - grp * EPI_COLS;  // valid columns from this half's start
-                for (int cc = 0; cc < EPI_COLS / 32; cc++) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + cc * 32, v);
+                for (int c2 = 0; c2 < EPI_COLS / (32 * LDG); c2++) {
+                    // LDG 32-column TMEM loads per wait (2 halves the exposed tcgen05.ld latency per tile)
+                    uint32_t vv[LDG][32];
+#pragma unroll
+                    for (int hh = 0; hh < LDG; hh++) tmem_ld32(taddr + c2 * (32 * LDG) + hh * 32, vv[hh]);
                     tmem_wait_ld();
+#pragma unroll
+                    for (int hh = 0; hh < LDG; hh++) {
+                    uint32_t (&v)[32] = vv[hh];
+                    const int cc = c2 * LDG + hh;
                     const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
                     const float4* pr4 = reinterpret_cast<const float4*>(pr + grp * EPI_COLS + cc * 32);
                     uint32_t mask = 0;
@@ -395,6 +401,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                                 atomicMin(p.gthr + q, kk);
                             }
                         }
+                    }
                     }
                 }
                 tcgen05_fence_before();

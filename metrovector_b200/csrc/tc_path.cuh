@@ -41,6 +41,7 @@ struct Buf {
 struct TcState {
     EncodeTiledFn encode = nullptr;
     Buf qprep, qconst, cand, lists, dump, gthr;
+    int ld_group = 1;              // TMEM loads issued per tcgen05.wait::ld in the epilogue (MVF_TC_LDG=1|2)
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
     int min_batch = 64;            // auto path: batches at least this large go to the tensor cores (MVF_TC_MIN_BATCH)
     bool attr_set = false;
@@ -65,6 +66,7 @@ inline void init(TcState& st) {
     st.encode = (EncodeTiledFn)fn;
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
+    if (const char* c = std::getenv("MVF_TC_LDG")) st.ld_group = std::atoi(c) == 2 ? 2 : 1;
 }
 
 inline int stages_for_cap(uint32_t cap) { return cap > 256 ? 3 : 4; }   // the sort scratch of k > 64 costs one operand stage
@@ -72,7 +74,11 @@ inline size_t smem_bytes(uint32_t cap) {
     return 1024 + (size_t)stages_for_cap(cap) * STAGE_BYTES + (EPI_THREADS / 32) * (size_t)cap * 8 + 2 * BN * 4 +
            (2 * MAX_STAGES + 4) * 8 + 16;
 }
-inline uint32_t cap_for_k(uint32_t k) { return k <= 16 ? 128u : k <= 64 ? 256u : 512u; }
+inline uint32_t cap_for_k(uint32_t k) {
+    static const int big = std::getenv("MVF_TC_BIGCAP") ? std::atoi(std::getenv("MVF_TC_BIGCAP")) : 0;
+    if (big) return k <= 16 ? 128u : k <= 64 ? 256u : 512u;
+    return k <= 16 ? 128u : k <= 112 ? 256u : 512u;   // cap >= k + 32 (one 32-column group) + headroom
+}
 
 // K2 takes f16 spaces with f16 queries and int8/uint8 spaces (any metric except integer cosine,
 // whose exact definition needs a division per element), k <= 128, rows of at least one K block.
@@ -88,14 +94,18 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
     return nq >= (uint32_t)st.min_batch && n >= 4096;
 }
 
-template <bool INT, int MODE>
+template <bool INT, int MODE, int LDG>
 inline const void* select_kernel_sc(int stages, int cl) {
-    if (stages == 3) return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 3, 2> : (const void*)gemm_topk_tc<INT, MODE, 3, 1>;
-    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 4, 2> : (const void*)gemm_topk_tc<INT, MODE, 4, 1>;
+    if (stages == 3) return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 3, 2, LDG> : (const void*)gemm_topk_tc<INT, MODE, 3, 1, LDG>;
+    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 4, 2, LDG> : (const void*)gemm_topk_tc<INT, MODE, 4, 1, LDG>;
 }
-inline const void* select_kernel(bool is_int, bool l2, int stages, int cl) {
-    if (is_int) return l2 ? select_kernel_sc<true, 0>(stages, cl) : select_kernel_sc<true, 1>(stages, cl);
-    return l2 ? select_kernel_sc<false, 0>(stages, cl) : select_kernel_sc<false, 1>(stages, cl);
+template <int LDG>
+inline const void* select_kernel_l(bool is_int, bool l2, int stages, int cl) {
+    if (is_int) return l2 ? select_kernel_sc<true, 0, LDG>(stages, cl) : select_kernel_sc<true, 1, LDG>(stages, cl);
+    return l2 ? select_kernel_sc<false, 0, LDG>(stages, cl) : select_kernel_sc<false, 1, LDG>(stages, cl);
+}
+inline const void* select_kernel(bool is_int, bool l2, int stages, int cl, int ldg) {
+    return ldg == 2 ? select_kernel_l<2>(is_int, l2, stages, cl) : select_kernel_l<1>(is_int, l2, stages, cl);
 }
 
 inline void make_map(TcState& st, CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint32_t d, uint64_t pitch,
@@ -168,7 +178,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
         p.dump = (float*)st.dump.p;
     }
     const bool l2 = a.metric == k::M_L2;
-    const void* fn = select_kernel(is_int, l2, cap > 256 ? 3 : 4, (int)CL);
+    const void* fn = select_kernel(is_int, l2, cap > 256 ? 3 : 4, (int)CL, st.ld_group);
     const size_t smem = smem_bytes(cap);
     TC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&map_q, (void*)&map_x, (void*)&p};
