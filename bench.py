@@ -52,6 +52,10 @@ ARITH = {0: "f32", 1: "f32", 2: "int32", 3: "int32"}
 METRIC_NAME = {0: "L2", 1: "InnerProduct", 2: "Cosine"}
 ES = {0: 4, 1: 2, 2: 1, 3: 1}
 DB_SEED, Q_SEED = 0x4D564631, 0x4D564632
+# DRAM traffic of the scan kernel per launch, from `ncu --set full` captures of these workloads
+# (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_ncu_{B,D,E}.md), as bytes per algorithmic
+# byte: B 3.0761e9 / 3.072e9, D 154.0147e9 / 153.6e9 (the extra 0.27% are the row norms), E 25.6043e9 / 25.6e9
+NCU_TRAFFIC_RATIO = {"B": 3.076061e9 / 3.072e9, "D": 154.014740e9 / 153.6e9, "E": 25.604293e9 / 25.6e9}
 
 
 def describe(wl, n, d, dt, metric, k, batch):
@@ -294,8 +298,11 @@ def main():
         bytes_per_launch = gs.local_n * d * es * (1 if prof["last_path"] == 2 else 1)
         launches_per_step = prof["scan_launches"] / max(1, args.steps)
         achieved = bytes_per_launch / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        ratio = NCU_TRAFFIC_RATIO.get(args.workload) if prof["last_path"] == 1 else None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "scan_topk" if prof["last_path"] == 1 else "gemm_topk_tc",
+                "traffic": (bytes_per_launch * ratio) if ratio else None,
+                "traffic_source": ("ncu --set full of this workload, profiles/r1_ncu_%s.md, scaled by rows" % args.workload) if ratio else None,
+                "peak_source": peak_src, "kernel": "scan_topk" if prof["last_path"] == 1 else "gemm_topk_tc",
                 "kernel_ms": scan_ms, "kernel_launches_per_step": launches_per_step,
                 "algorithmic_bytes_per_launch": bytes_per_launch}
         if prof["last_path"] == 2:
