@@ -1,0 +1,98 @@
+"""Parity at BASELINE.json's full sizes, through size-independent properties (the CPU oracle cannot
+scan 1e6..1e9 rows in a test, but it can regenerate and score any single row of the synthetic spaces).
+
+Properties checked on device-generated spaces:
+  * planted queries: a query equal to stored row r returns r first with the metric's identity score;
+  * score consistency: every returned (id, score) pair equals the oracle's score of that regenerated row
+    (bit-exact for integers, within the float tolerance otherwise), and the list is sorted best-first;
+  * sampled completeness: no row of a 200k-row oracle-scanned sample beats the returned k-th score;
+  * shard additivity: searching two half spaces (row_base applied) and merging on the host equals
+    searching the whole space -- the single-GPU form of the multi-GPU identity.
+"""
+import numpy as np
+import pytest
+
+import metrovector_b200 as mv
+import oracle
+from util import as_query
+
+pytestmark = pytest.mark.gpu
+SEED = 0x4D564631
+
+
+def _check_consistency(dtype, metric, d, q, ids, sc, isc):
+    is_int = dtype in (oracle.I8, oracle.U8)
+    for gid, s, si in zip(ids, sc, isc):
+        row = mv.synth_fill_host(dtype, SEED, int(gid), 1, d)[0]
+        ref, iref, _ = oracle.score_row(row, dtype, metric, q)
+        if is_int and metric != oracle.COS:
+            assert si == iref and s == np.float32(iref)
+        elif is_int:
+            assert np.float32(s).view(np.uint32) == np.float32(ref).view(np.uint32)
+        else:
+            assert abs(float(s) - ref) <= 2e-5 * max(1.0, abs(ref)), (gid, s, ref)
+    rank = -sc if metric == oracle.IP else sc
+    assert np.all(np.diff(rank) >= 0)
+
+
+@pytest.mark.parametrize("name,n,d,dtype,metric,k", [
+    ("B", 1_000_000, 768, oracle.F32, oracle.L2, 10),            # BASELINE configs[1], full size
+    ("A", 100_000, 128, oracle.F32, oracle.COS, 10),             # configs[0], full size
+    ("D-slab", 12_500_000, 768, oracle.F16, oracle.COS, 10),     # one 8-GPU shard of configs[3]
+    ("E-slab", 125_000_000, 128, oracle.U8, oracle.L2, 10),      # one 8-GPU shard of configs[4]
+])
+def test_full_size_properties(engine, name, n, d, dtype, metric, k):
+    gs = engine.synthetic(mv.DataType(dtype), mv.DistanceMetric(metric), n, d, SEED)
+    planted = [0, n // 3, n - 1]
+    qrows = [mv.synth_fill_host(dtype, SEED, r, 1, d)[0] for r in planted]
+    qrand = mv.synth_fill_host(dtype, SEED + 1, 0, 2, d)
+    queries = np.stack([as_query(dtype, r) for r in qrows + list(qrand)])
+    ids, sc, isc = gs.search(queries, k)
+    for i, r in enumerate(planted):
+        assert ids[i][0] == r, (name, r, ids[i])
+        if metric == oracle.L2:
+            assert sc[i][0] == 0.0
+        else:
+            assert abs(sc[i][0]) <= 2e-5
+    for i in range(len(queries)):
+        assert len(set(ids[i].tolist())) == k and ids[i].max() < n
+        _check_consistency(dtype, metric, d, queries[i], ids[i], sc[i], isc[i])
+    # sampled completeness on the two random queries
+    sample_n = min(n, 200_000)
+    sample = mv.synth_fill_host(dtype, SEED, n - sample_n, sample_n, d)
+    for i in (3, 4):
+        o_ids, o_sc, o_isc = oracle.topk(sample, dtype, metric, queries[i], 1, row_base=n - sample_n)
+        best_in_sample = o_sc[0]
+        kth = sc[i][k - 1]
+        if metric == oracle.IP:
+            assert best_in_sample <= sc[i][0] + 1e-3 * abs(sc[i][0])
+        else:
+            assert best_in_sample >= sc[i][0] - 2e-5 * max(1.0, abs(float(sc[i][0])))
+            if best_in_sample < kth - 2e-5 * max(1.0, abs(float(kth))):
+                assert int(o_ids[0]) in ids[i].tolist()
+    gs.free()
+
+
+@pytest.mark.parametrize("n,d,dtype,metric", [(1_000_000, 768, oracle.F32, oracle.L2), (20_000_000, 128, oracle.U8, oracle.L2)])
+def test_shard_additivity_at_size(engine, n, d, dtype, metric):
+    k, nq = 10, 3
+    queries = np.stack([as_query(dtype, r) for r in mv.synth_fill_host(dtype, SEED + 1, 0, nq, d)])
+    whole = engine.synthetic(mv.DataType(dtype), mv.DistanceMetric(metric), n, d, SEED)
+    w_ids, w_sc, w_isc = whole.search(queries, k)
+    whole.free()
+    # two "ranks" on one GPU: upload each half with its row_base, merge (score, id) on the host
+    half = n // 2
+    parts = []
+    for base, cnt in ((0, half), (half, n - half)):
+        rows = mv.synth_fill_host(dtype, SEED, base, cnt, d)
+        gs = engine.from_host(rows, mv.DataType(dtype), mv.DistanceMetric(metric), row_base=base, global_n=n)
+        parts.append(gs.search(queries, k))
+        gs.free()
+    for qi in range(nq):
+        cand = {}
+        for ids, sc, isc in parts:
+            for gid, s, si in zip(ids[qi], sc[qi], isc[qi]):
+                cand[int(gid)] = (float(s), int(si))
+        merged = sorted(cand.items(), key=lambda kv: (kv[1][0], kv[0]))[:k]
+        assert [m[0] for m in merged] == w_ids[qi].tolist()
+        assert [m[1][0] for m in merged] == [float(x) for x in w_sc[qi]]
