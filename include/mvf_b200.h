@@ -172,6 +172,8 @@ MVF_API int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64
                                uint64_t* global_n, uint32_t* dimension, int* data_type, int* metric);
 /* how the rows got to HBM: path 1 = cudaHostRegister'd mapping, 2 = pinned staging, 0 = generated */
 MVF_API int mvf_gpu_space_upload_stats(const mvf_gpu_space* s, int* path, double* seconds, uint64_t* bytes);
+/* diagnostic: why the mapping was not page-locked in place (empty string when it was, or for generated spaces) */
+MVF_API const char* mvf_gpu_space_upload_note(const mvf_gpu_space* s);
 /* copy rows / norms back (tests: device bytes == mapped bytes) */
 MVF_API int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out);
 MVF_API int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out_sq);

@@ -467,7 +467,10 @@ class GpuSpace:
     def upload_stats(self):
         p, s, b = _INT(), _c.c_double(), _U64()
         _check(_lib.mvf_gpu_space_upload_stats(self._h, _c.byref(p), _c.byref(s), _c.byref(b)))
-        return dict(path=p.value, seconds=s.value, bytes=b.value)
+        _lib.mvf_gpu_space_upload_note.restype = _c.c_char_p
+        _lib.mvf_gpu_space_upload_note.argtypes = [_P]
+        note = (_lib.mvf_gpu_space_upload_note(self._h) or b"").decode()
+        return dict(path=p.value, seconds=s.value, bytes=b.value, note=note)
 
     def read_rows(self, start, count):
         out = np.empty((count, self.dimension), dtype=_NP_DTYPE[self.data_type])

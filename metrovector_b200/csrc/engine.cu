@@ -5,13 +5,16 @@
 // entry point fails with MVF_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "c_api_common.hpp"
@@ -99,6 +102,8 @@ struct mvf_gpu {
     DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2];
     int merge_tmp_flip = 0;
     unsigned char* pinned_out = nullptr;   // 64 KiB pinned mirror for small results
+    std::vector<unsigned char*> stage_pool;   // pinned staging buffers (16 MiB each), kept across uploads
+    int upload_threads = 8;                // MVF_UPLOAD_THREADS
     std::map<std::pair<const void*, size_t>, int> occ_cache;
     mvf::tc::TcState tc;
 };
@@ -113,6 +118,7 @@ struct mvf_gpu_space {
     float* sq = nullptr;
     int upload_path = 0;       // 0 none/synthetic, 1 cudaHostRegister'd mapping, 2 pinned staging
     double upload_seconds = 0.0;
+    std::string upload_note;   // why the in-place registration was not used, if it was not
 };
 
 namespace {
@@ -427,7 +433,10 @@ void upload_rows(mvf_gpu_space* s, const unsigned char* src, uint64_t nrows, siz
         uintptr_t lo = (uintptr_t)a & ~(uintptr_t)(page - 1);
         uintptr_t hi = ((uintptr_t)a + cnt * rowbytes + page - 1) & ~(uintptr_t)(page - 1);
         cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterReadOnly);
-        if (e != cudaSuccess) { cudaGetLastError(); registered_ok = false; break; }
+        if (e != cudaSuccess) {
+            s->upload_note = std::string("cudaHostRegister(read-only) refused: ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+            cudaGetLastError(); registered_ok = false; break;
+        }
         try {
             copy_rows(a, r, cnt);
             CUDA_CHECK(cudaStreamSynchronize(g->stream));
@@ -437,32 +446,71 @@ void upload_rows(mvf_gpu_space* s, const unsigned char* src, uint64_t nrows, siz
         r += cnt;
     }
     if (r < nrows) {
+        // pinned staging, several host threads: each owns two staging buffers and a stream, copies
+        // its share of the row chunks out of the mapping and queues the H2D copy behind it
         s->upload_path = 2;
-        const size_t stage_bytes = std::max<size_t>(32u << 20, rowbytes);
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));          // the padding memset above is ordered first
+        const size_t stage_bytes = std::max<size_t>(16u << 20, rowbytes);
         const uint64_t stage_rows = stage_bytes / rowbytes;
-        unsigned char* stage[2] = {nullptr, nullptr};
-        cudaEvent_t ev[2] = {nullptr, nullptr};
-        try {
-            for (int i = 0; i < 2; i++) {
-                CUDA_CHECK(cudaMallocHost((void**)&stage[i], stage_rows * rowbytes));
-                CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-            }
-            int b = 0;
-            while (r < nrows) {
-                uint64_t cnt = std::min<uint64_t>(stage_rows, nrows - r);
-                CUDA_CHECK(cudaEventSynchronize(ev[b]));
-                std::memcpy(stage[b], src + r * rowbytes, cnt * rowbytes);
-                copy_rows(stage[b], r, cnt);
-                CUDA_CHECK(cudaEventRecord(ev[b], g->stream));
-                r += cnt; b ^= 1;
-            }
-            CUDA_CHECK(cudaStreamSynchronize(g->stream));
-        } catch (...) {
-            cudaStreamSynchronize(g->stream);
-            for (int i = 0; i < 2; i++) { if (stage[i]) cudaFreeHost(stage[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
-            throw;
+        const uint64_t first = r, chunks = (nrows - first + stage_rows - 1) / stage_rows;
+        const int nthreads = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->upload_threads, chunks));
+        // the kernel should read ahead: the mapping is consumed front to back exactly once
+        {
+            const long page = 4096;
+            uintptr_t lo = (uintptr_t)(src + first * rowbytes) & ~(uintptr_t)(page - 1);
+            madvise((void*)lo, (uintptr_t)(src + nrows * rowbytes) - lo, MADV_SEQUENTIAL);
+            madvise((void*)lo, (uintptr_t)(src + nrows * rowbytes) - lo, MADV_WILLNEED);
         }
-        for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); cudaEventDestroy(ev[i]); }
+        const bool pooled = stage_bytes == (16u << 20);
+        if (pooled) {
+            while (g->stage_pool.size() < (size_t)nthreads * 2) {
+                unsigned char* b = nullptr;
+                CUDA_CHECK(cudaMallocHost((void**)&b, 16u << 20));
+                g->stage_pool.push_back(b);
+            }
+        }
+        std::vector<std::thread> workers;
+        std::mutex err_mu;
+        std::string err;
+        const int device = g->device;
+        for (int t = 0; t < nthreads; t++) {
+            workers.emplace_back([&, t] {
+                unsigned char* stage[2] = {nullptr, nullptr};
+                cudaEvent_t ev[2] = {nullptr, nullptr};
+                cudaStream_t st = nullptr;
+                auto fail = [&](cudaError_t ce, const char* what) {
+                    std::lock_guard<std::mutex> lk(err_mu);
+                    if (err.empty()) err = std::string(cudaGetErrorName(ce)) + ": " + cudaGetErrorString(ce) + " at " + what;
+                };
+                cudaError_t ce = cudaSetDevice(device);
+                if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+                for (int i = 0; i < 2 && ce == cudaSuccess; i++) {
+                    if (pooled) stage[i] = g->stage_pool[(size_t)t * 2 + i];
+                    else ce = cudaMallocHost((void**)&stage[i], stage_rows * rowbytes);
+                    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+                }
+                if (ce != cudaSuccess) fail(ce, "staging setup");
+                int b = 0;
+                for (uint64_t c = (uint64_t)t; c < chunks && ce == cudaSuccess; c += (uint64_t)nthreads) {
+                    const uint64_t r0 = first + c * stage_rows;
+                    const uint64_t cnt = std::min<uint64_t>(stage_rows, nrows - r0);
+                    ce = cudaEventSynchronize(ev[b]);
+                    if (ce != cudaSuccess) { fail(ce, "cudaEventSynchronize"); break; }
+                    std::memcpy(stage[b], src + r0 * rowbytes, cnt * rowbytes);
+                    unsigned char* dst = s->rows + r0 * pitch;
+                    if (pitch == rowbytes) ce = cudaMemcpyAsync(dst, stage[b], cnt * rowbytes, cudaMemcpyHostToDevice, st);
+                    else ce = cudaMemcpy2DAsync(dst, pitch, stage[b], rowbytes, rowbytes, cnt, cudaMemcpyHostToDevice, st);
+                    if (ce == cudaSuccess) ce = cudaEventRecord(ev[b], st);
+                    if (ce != cudaSuccess) { fail(ce, "staged copy"); break; }
+                    b ^= 1;
+                }
+                if (st) cudaStreamSynchronize(st);
+                for (int i = 0; i < 2; i++) { if (!pooled && stage[i]) cudaFreeHost(stage[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+                if (st) cudaStreamDestroy(st);
+            });
+        }
+        for (auto& w : workers) w.join();
+        if (!err.empty()) throw MvfError::cuda(err);
     }
     s->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -502,6 +550,7 @@ int mvf_gpu_init(int device, mvf_gpu** out) {
         if (se != cudaSuccess) { delete g; CUDA_CHECK(se); }
         g->own_stream = true;
         if (const char* c = std::getenv("MVF_SCAN_CTAS_PER_SM")) g->ctas_per_sm_cap = std::atoi(c);
+        if (const char* c = std::getenv("MVF_UPLOAD_THREADS")) g->upload_threads = std::max(1, std::min(16, std::atoi(c)));
         *out = g;
     });
 }
@@ -516,6 +565,7 @@ void mvf_gpu_shutdown(mvf_gpu* g) {
     g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release();
     mvf::tc::release(g->tc);
     if (g->pinned_out) cudaFreeHost(g->pinned_out);
+    for (auto* b : g->stage_pool) cudaFreeHost(b);
     if (g->own_stream) cudaStreamDestroy(g->stream);
     delete g;
 }
@@ -654,6 +704,8 @@ int mvf_gpu_space_upload_stats(const mvf_gpu_space* s, int* path, double* second
         if (bytes) *bytes = s->local_n * (uint64_t)s->d * element_size((DataType)s->dtype);
     });
 }
+
+const char* mvf_gpu_space_upload_note(const mvf_gpu_space* s) { return s ? s->upload_note.c_str() : ""; }
 
 int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out) {
     return guard([&] {

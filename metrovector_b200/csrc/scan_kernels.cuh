@@ -1,6 +1,8 @@
 // scan_kernels.cuh -- K1, the bandwidth-bound scan with fused top-k (templates; instantiated per
 // data type in scan_f32.cu / scan_f16.cu / scan_i8.cu / scan_u8.cu so the build parallelises).
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace mvf {
@@ -202,6 +204,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
         for (int r = 0; r < R; r++) x[r] = ldg_stream16(ptr + (size_t)r * pitch);
         if (p.metric == M_COS) xn = p.norm[g * R + myrow];
     }
+    // the row loop is compiled twice: ragged rows (chunk count not a multiple of 32) zero the lanes past
+    // the row end when a tile is consumed; the common shapes skip that work entirely
+    auto run = [&](auto ragged_tag) {
+    constexpr bool RAGGED = decltype(ragged_tag)::value;
     while (g < groups) {
         const uint32_t gn = g + gstride;
         const bool more = gn < groups && gn > g;
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
             const uint32_t ci = c * 32 + lane;
             // ragged rows: lanes past the row end read whatever follows (always inside the padded
             // buffer) and the tile is zeroed when consumed
-            const bool dead = ragged && ci >= C;
+            const bool dead = RAGGED && ci >= C;
             float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
             for (int r = 0; r < R; r++) {
                 uint4 cur = x[r];
                 x[r] = ldg_stream16(tp + (size_t)r * pitch);
-                if (dead) cur = make_uint4(0, 0, 0, 0);
+                if (RAGGED && dead) cur = make_uint4(0, 0, 0, 0);
                 if (F) {
                     float xf[EPC];
                     widen<DT>(cur, xf);
@@ -287,6 +293,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
         }
         g = more ? gn : groups; ptr = ptr_n; xn = xn_n;
     }
+    };
+    if (ragged) run(std::true_type{}); else run(std::false_type{});
     emit_cta_lists<NQ>(p, lists);
 }
 

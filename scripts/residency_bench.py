@@ -28,7 +28,7 @@ q = mv.synth_fill_host(0, 0x4D564632, 0, 4, d)
 ref_space = eng.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, n, d, 0x4D564631)
 ref = ref_space.search(q, 10)
 out = {"rows": n, "file_gb": os.path.getsize(path) / 1e9, "host_fill_s": t1 - t0, "write_s": t2 - t1, "uploads": []}
-for no_reg in ("", "1"):
+for no_reg in ("", "1", "1"):
     if no_reg:
         os.environ["MVF_NO_HOST_REGISTER"] = "1"
     r = mv.MvfReader.open(path)
@@ -42,7 +42,7 @@ for no_reg in ("", "1"):
     rows_ok = bool(np.array_equal(gs.read_rows(n - 3, 3), rows[-3:]))
     out["uploads"].append({"path": {1: "cudaHostRegister(read-only mapping)", 2: "pinned staging"}[st["path"]],
                            "seconds": st["seconds"], "gb_per_s": st["bytes"] / 1e9 / st["seconds"], "wall_s": t4 - t3,
-                           "search_identical_to_generated_space": same, "tail_rows_identical": rows_ok})
+                           "search_identical_to_generated_space": same, "tail_rows_identical": rows_ok, "note": st["note"]})
     gs.free()
     r.close()
 os.remove(path)
