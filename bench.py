@@ -115,7 +115,7 @@ def cpu_scan_qps(n, d, dt, metric, k, budget_rows):
     threads = os.cpu_count() or 1
     sample = int(min(n, budget_rows))
     db = oracle.synth(dt, DB_SEED, 0, sample, d, threads=threads)
-    q = oracle.synth(dt, Q_SEED, 0, 2, d)
+    q = oracle.synth(dt, Q_SEED, 0, 4, d)
     if dt in (0, 1):
         q = q.astype(np.float32)
     oracle.scan_timed(db, dt, metric, q[:1], k, threads)            # warm the pages
@@ -333,7 +333,7 @@ def main():
         }
         if world == 1 and not args.no_cpu:
             try:
-                qps, cores, sample, tq = cpu_scan_qps(n, d, dt, metric, k, budget_rows=max(4096, (1 << 30) // (d * es)))
+                qps, cores, sample, tq = cpu_scan_qps(n, d, dt, metric, k, budget_rows=max(4096, (2 << 30) // (d * es)))
                 line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                         "sample": "%d of %d rows, %.3f s per query on the sample, scaled linearly" % (sample, n, tq)}
             except Exception as ex:
