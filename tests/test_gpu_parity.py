@@ -107,6 +107,20 @@ def test_sweep_shapes(engine, dtype, metric):
         gs.free()
 
 
+@pytest.mark.parametrize("k", [128, 200, 300, 752, 800, 1024])
+def test_large_k_exercises_every_merge_flavour(engine, k):
+    # many per-CTA lists x large k: single tournament (k=128), segmented tournament (200..752),
+    # block-bitonic rounds (k > 752)
+    for dtype, n, d in ((oracle.U8, 120_000, 16), (oracle.F32, 60_000, 40)):
+        db = mv.synth_fill_host(dtype, 61, 0, n, d)
+        gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+        q = np.stack([as_query(dtype, r) for r in mv.synth_fill_host(dtype, 62, 0, 3, d)])
+        for metric in (oracle.L2, oracle.COS):
+            ids, sc, isc = gs.search(q, k, metric=metric)
+            check_batch(db, dtype, metric, q, k, ids, sc, isc)
+        gs.free()
+
+
 def test_ties_resolve_to_lowest_index(engine):
     # 3 distinct byte values -> thousands of exact ties in every metric
     rng = np.random.default_rng(5)

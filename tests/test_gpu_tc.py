@@ -50,7 +50,7 @@ def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
     engine.set_path(2)
     try:
         metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)
-        for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33)):
+        for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33), (130, 128)):
             q = mv.synth_fill_host(dtype, 42, 0, nq, d)
             q[0] = db[n // 2]
             for metric in metrics:
