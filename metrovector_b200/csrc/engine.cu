@@ -101,7 +101,8 @@ struct mvf_gpu {
     int ctas_per_sm_cap = 0;   // MVF_SCAN_CTAS_PER_SM, 0 = occupancy
     DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2];
     int merge_tmp_flip = 0;
-    unsigned char* pinned_out = nullptr;   // 64 KiB pinned mirror for small results
+    unsigned char* pinned_out = nullptr;   // 64 KiB mapped pinned block small results are written into by the merge kernel
+    unsigned char* pinned_out_dev = nullptr;
     std::vector<unsigned char*> stage_pool;   // pinned staging buffers (16 MiB each), kept across uploads
     int upload_threads = 8;                // MVF_UPLOAD_THREADS
     std::map<std::pair<const void*, size_t>, int> occ_cache;
@@ -745,22 +746,29 @@ int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint3
         g->queries.reserve(std::max<size_t>(qbytes, 16));
         // results live in one device block [ids | scores | iscores]; small results come back in a single
         // D2H copy through a pinned mirror (one driver call instead of three), large ones directly
-        g->out_ids.reserve(cnt * 16);
-        unsigned char* dev = (unsigned char*)g->out_ids.p;
-        uint64_t* d_ids = (uint64_t*)dev;
-        float* d_scores = (float*)(dev + cnt * 8);
-        int32_t* d_isc = (int32_t*)(dev + cnt * 12);
-        CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
-        search_device(s, g->queries.p, query_dtype, nq, k, metric, d_ids, d_scores, out_iscores ? d_isc : nullptr);
         const size_t back = cnt * (out_iscores ? 16 : 12);
+        CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
         if (back <= 64 * 1024) {
-            if (!g->pinned_out) CUDA_CHECK(cudaMallocHost((void**)&g->pinned_out, 64 * 1024));
-            CUDA_CHECK(cudaMemcpyAsync(g->pinned_out, dev, back, cudaMemcpyDeviceToHost, g->stream));
+            // small results: the merge kernel stores straight into mapped pinned host memory, so the only
+            // host<->device traffic calls are the query copy and the stream sync
+            if (!g->pinned_out) {
+                CUDA_CHECK(cudaHostAlloc((void**)&g->pinned_out, 64 * 1024, cudaHostAllocMapped));
+                CUDA_CHECK(cudaHostGetDevicePointer((void**)&g->pinned_out_dev, g->pinned_out, 0));
+            }
+            unsigned char* dev = g->pinned_out_dev;
+            search_device(s, g->queries.p, query_dtype, nq, k, metric, (uint64_t*)dev, (float*)(dev + cnt * 8),
+                          out_iscores ? (int32_t*)(dev + cnt * 12) : nullptr);
             CUDA_CHECK(cudaStreamSynchronize(g->stream));
             std::memcpy(out_ids, g->pinned_out, cnt * 8);
             if (out_scores) std::memcpy(out_scores, g->pinned_out + cnt * 8, cnt * 4);
             if (out_iscores) std::memcpy(out_iscores, g->pinned_out + cnt * 12, cnt * 4);
         } else {
+            g->out_ids.reserve(cnt * 16);
+            unsigned char* dev = (unsigned char*)g->out_ids.p;
+            uint64_t* d_ids = (uint64_t*)dev;
+            float* d_scores = (float*)(dev + cnt * 8);
+            int32_t* d_isc = (int32_t*)(dev + cnt * 12);
+            search_device(s, g->queries.p, query_dtype, nq, k, metric, d_ids, d_scores, out_iscores ? d_isc : nullptr);
             CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids, cnt * 8, cudaMemcpyDeviceToHost, g->stream));
             if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, d_scores, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
             if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, d_isc, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
