@@ -178,6 +178,19 @@ MVF_API const char* mvf_gpu_space_upload_note(const mvf_gpu_space* s);
 MVF_API int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out);
 MVF_API int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out_sq);
 
+/* Integrity (the finished intent of MvfReader::validate_with_checksum, src/reader.rs:172-221, on the
+ * device): CRC-32/IEEE of the resident rows computed by a CUDA kernel; _verify compares it with the
+ * block manifest entry the builder wrote (src/builder.rs:251) -> MVF_ERR_CORRUPTED_DATA on mismatch. */
+MVF_API int mvf_gpu_space_checksum(mvf_gpu_space* s, uint32_t* out_crc, double* out_kernel_ms);
+MVF_API int mvf_gpu_space_verify_checksum(mvf_gpu_space* s, const mvf_space* file_space);
+
+/* The rows behind a result list, from the HBM copy: the `vector` field of ScoredVector
+ * (examples/similarity_search.rs:18) / VectorSpace::get_vectors_batch (src/vectors/vector_space.rs:230-243).
+ * ids are global row ids; out receives count rows, raw (as_f32 = 0) or widened like Vector::as_f32
+ * (as_f32 = 1; Int8/UInt8 -> MVF_ERR_BUILD like src/vectors/vector.rs:90).  Ids outside this rank's
+ * shard (and the UINT64_MAX padding of short result lists) give zero rows. */
+MVF_API int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uint32_t count, int as_f32, void* out);
+
 /* find_top_k_similar(space, query, k), examples/similarity_search.rs:140-176, for nq queries at
  * once.  queries: nq x dimension, HOST memory, dtype query_dtype (MVF_FLOAT32, or the space's own
  * dtype; integer spaces take only their own dtype).  metric: MVF_METRIC_SPACE_DEFAULT or an

@@ -135,6 +135,9 @@ _SIGS = {
     "mvf_gpu_space_read_norms": [_P, _P, _P],
     "mvf_gpu_search": [_P, _P, _INT, _U32, _U32, _INT, _P, _P, _P],
     "mvf_gpu_search_device": [_P, _P, _INT, _U32, _U32, _INT, _P, _P, _P],
+    "mvf_gpu_space_checksum": [_P, _c.POINTER(_U32), _c.POINTER(_c.c_double)],
+    "mvf_gpu_space_verify_checksum": [_P, _P],
+    "mvf_gpu_space_get_vectors": [_P, _P, _U32, _INT, _P],
     "mvf_gpu_tc_dump": [_P, _P, _INT, _U32, _U32, _INT, _P, _U64, _c.POINTER(_U32), _c.POINTER(_U32)],
     "mvf_gpu_set_path": [_P, _INT],
     "mvf_gpu_profile": [_P, _INT],
@@ -482,6 +485,24 @@ class GpuSpace:
         sq = np.empty(self.local_n, dtype=np.float32)
         _check(_lib.mvf_gpu_space_read_norms(self._h, norm.ctypes.data_as(_P), sq.ctypes.data_as(_P)))
         return norm, sq
+
+    def checksum(self):
+        """CRC-32/IEEE of the resident rows, computed on the device.  Returns (crc, kernel_ms)."""
+        crc, ms = _U32(), _c.c_double()
+        _check(_lib.mvf_gpu_space_checksum(self._h, _c.byref(crc), _c.byref(ms)))
+        return crc.value, ms.value
+
+    def verify_checksum(self, space):
+        """Device CRC of the resident block against the file's block manifest (raises CorruptedData)."""
+        _check(_lib.mvf_gpu_space_verify_checksum(self._h, space._h))
+
+    def get_vectors(self, ids, as_f32=False):
+        """Rows of the HBM copy for global row ids (the `vector` field of the reference's ScoredVector)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64).ravel()
+        dt = np.float32 if as_f32 else _NP_DTYPE[self.data_type]
+        out = np.empty((len(ids), self.dimension), dtype=dt)
+        _check(_lib.mvf_gpu_space_get_vectors(self._h, ids.ctypes.data_as(_P), len(ids), 1 if as_f32 else 0, out.ctypes.data_as(_P)))
+        return out
 
     def _query_array(self, queries):
         q = np.asarray(queries)

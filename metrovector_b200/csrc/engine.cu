@@ -99,7 +99,7 @@ struct mvf_gpu {
     uint64_t scan_launches = 0, all_launches = 0;
     int last_path = 0;
     int ctas_per_sm_cap = 0;   // MVF_SCAN_CTAS_PER_SM, 0 = occupancy
-    DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2];
+    DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2], gather_ids, gather_out, crc_tables;
     int merge_tmp_flip = 0;
     unsigned char* pinned_out = nullptr;   // 64 KiB mapped pinned block small results are written into by the merge kernel
     unsigned char* pinned_out_dev = nullptr;
@@ -563,7 +563,7 @@ void mvf_gpu_shutdown(mvf_gpu* g) {
     if (g->comm) { try { nccl().CommDestroy(g->comm); } catch (...) {} }
     for (auto& e : g->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     g->cand.release(); g->packed_local.release(); g->gathered.release(); g->queries.release();
-    g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release();
+    g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release(); g->gather_ids.release(); g->gather_out.release(); g->crc_tables.release();
     mvf::tc::release(g->tc);
     if (g->pinned_out) cudaFreeHost(g->pinned_out);
     for (auto* b : g->stage_pool) cudaFreeHost(b);
@@ -725,6 +725,112 @@ int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out
         CUDA_CHECK(cudaStreamSynchronize(s->g->stream));
         if (out_norm) CUDA_CHECK(cudaMemcpy(out_norm, s->norm, s->local_n * 4, cudaMemcpyDeviceToHost));
         if (out_sq) CUDA_CHECK(cudaMemcpy(out_sq, s->sq, s->local_n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+// CRC-32 of the resident rows, computed on the device (rows must be resident without padding, i.e. row
+// bytes a multiple of 16, and the space must not be sharded)
+int mvf_gpu_space_checksum(mvf_gpu_space* s, uint32_t* out_crc, double* out_ms) {
+    return guard([&] {
+        mvf_gpu* g = s->g;
+        const size_t rowbytes = (size_t)s->d * element_size((DataType)s->dtype);
+        if (rowbytes != s->pitch) throw MvfError::build_error("device checksum needs rows of a multiple of 16 bytes");
+        if (s->local_n != s->global_n) throw MvfError::build_error("device checksum needs the whole space on one GPU");
+        CUDA_CHECK(cudaSetDevice(g->device));
+        if (!g->crc_tables.p) {
+            // slicing-by-8 tables + x^(2^k) mod P, built once on the host
+            std::vector<uint32_t> tab(8 * 256 + 64);
+            for (uint32_t i = 0; i < 256; i++) {
+                uint32_t c = i;
+                for (int b = 0; b < 8; b++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+                tab[i] = c;
+            }
+            for (uint32_t i = 0; i < 256; i++)
+                for (int t = 1; t < 8; t++) tab[t * 256 + i] = (tab[(t - 1) * 256 + i] >> 8) ^ tab[tab[(t - 1) * 256 + i] & 0xff];
+            auto mul = [](uint32_t a, uint32_t b) {
+                uint32_t p = 0;
+                for (int i = 31; i >= 0; i--) { if (a & (1u << i)) p ^= b; b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1; }
+                return p;
+            };
+            uint32_t x = 0x40000000u;                        // x^1
+            for (int kb = 0; kb < 64; kb++) { tab[8 * 256 + kb] = x; x = mul(x, x); }
+            g->crc_tables.reserve(tab.size() * 4 + 16);
+            CUDA_CHECK(cudaMemcpyAsync(g->crc_tables.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, g->stream));
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        }
+        k::CrcParams p;
+        p.data = s->rows; p.nbytes = (uint64_t)s->local_n * rowbytes;
+        const uint64_t threads_target = (uint64_t)g->sm_count * 512;
+        uint64_t seg = (p.nbytes + threads_target - 1) / threads_target;
+        seg = std::max<uint64_t>(256, (seg + 127) & ~127ull);
+        p.seg_len = seg;
+        p.tables = (const uint32_t*)g->crc_tables.p; p.x2n = p.tables + 8 * 256;
+        p.out = (uint32_t*)((unsigned char*)g->crc_tables.p + (8 * 256 + 64) * 4);
+        CUDA_CHECK(cudaMemsetAsync(p.out, 0, 4, g->stream));
+        const uint64_t nthreads = (p.nbytes + seg - 1) / seg;
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, (nthreads + 255) / 256);
+        cudaEvent_t a, b; CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+        cudaEventRecord(a, g->stream);
+        k::crc32_resident<<<grid, 256, 0, g->stream>>>(p);
+        cudaEventRecord(b, g->stream);
+        CUDA_CHECK(cudaGetLastError());
+        g->all_launches++;
+        uint32_t crc = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&crc, p.out, 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        float ms = 0.f; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b);
+        if (out_crc) *out_crc = crc;
+        if (out_ms) *out_ms = ms;
+    });
+}
+
+// integrity on upload: device CRC of the resident block against the manifest entry of the file
+int mvf_gpu_space_verify_checksum(mvf_gpu_space* s, const mvf_space* sp) {
+    return guard([&] {
+        const VectorSpace& vs = sp->vs;
+        const auto& blocks = vs.reader()->blocks();
+        const SpaceInfo* info = nullptr;
+        for (const auto& si : vs.reader()->spaces()) if (&si.name == &vs.name()) info = &si;
+        if (!info || info->vectors_block_index >= blocks.size()) throw MvfError::corrupted_data("Invalid vector block index");
+        const DataBlock& blk = blocks[info->vectors_block_index];
+        const uint64_t resident = (uint64_t)s->local_n * s->d * element_size((DataType)s->dtype);
+        if (blk.checksum == 0) return;                               // nothing recorded (src/reader.rs:183)
+        if (resident != blk.size) throw MvfError::build_error("resident rows do not cover the whole block (total_vectors < block rows)");
+        uint32_t crc = 0;
+        int rc = mvf_gpu_space_checksum(s, &crc, nullptr);
+        if (rc != MVF_OK) throw MvfError((ErrorKind)rc, mvf_last_error());
+        if (crc != blk.checksum)
+            throw MvfError::corrupted_data("Block checksum mismatch: expected " + std::to_string(blk.checksum) + ", got " + std::to_string(crc));
+    });
+}
+
+int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uint32_t count, int as_f32, void* out) {
+    return guard([&] {
+        mvf_gpu* g = s->g;
+        if (!count) return;
+        if (!ids || !out) throw MvfError::build_error("null argument");
+        const bool fl = s->dtype == k::DT_F32 || s->dtype == k::DT_F16;
+        if (as_f32 && !fl) throw MvfError::build_error("Cannot convert to f32");     // Vector::as_f32, src/vectors/vector.rs:90
+        CUDA_CHECK(cudaSetDevice(g->device));
+        const size_t obytes = (size_t)count * s->d * (as_f32 ? 4 : element_size((DataType)s->dtype));
+        g->gather_ids.reserve((size_t)count * 8);
+        g->gather_out.reserve(obytes);
+        CUDA_CHECK(cudaMemcpyAsync(g->gather_ids.p, ids, (size_t)count * 8, cudaMemcpyHostToDevice, g->stream));
+        const uint32_t grid = std::min<uint32_t>((count + 7) / 8, (uint32_t)g->sm_count * 8);
+        const uint64_t* di = (const uint64_t*)g->gather_ids.p;
+        unsigned char* dout = (unsigned char*)g->gather_out.p;
+#define MVF_GATHER(DTV, F32V) k::gather_rows<DTV, F32V><<<grid, 256, 0, g->stream>>>(s->rows, s->pitch, s->d, s->local_n, s->row_base, di, count, dout)
+        switch (s->dtype) {
+            case k::DT_F32: if (as_f32) MVF_GATHER(k::DT_F32, true); else MVF_GATHER(k::DT_F32, false); break;
+            case k::DT_F16: if (as_f32) MVF_GATHER(k::DT_F16, true); else MVF_GATHER(k::DT_F16, false); break;
+            case k::DT_I8: MVF_GATHER(k::DT_I8, false); break;
+            default: MVF_GATHER(k::DT_U8, false); break;
+        }
+#undef MVF_GATHER
+        CUDA_CHECK(cudaGetLastError());
+        g->all_launches++;
+        CUDA_CHECK(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
     });
 }
 

@@ -323,6 +323,106 @@ __global__ void __launch_bounds__(256) row_norms(const unsigned char* rows, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// crc32_resident -- CRC-32 (IEEE 802.3, what crc32fast::hash writes into the block manifest,
+// src/builder.rs:251) of the resident rows, the check the reference's validate_with_checksum
+// (src/reader.rs:172-221) never finished.  Every thread hashes one contiguous segment with
+// slicing-by-8 tables in shared memory; a segment CRC is moved to its place in the whole message by
+// multiplying with x^(8 * bytes_after) mod P (the zlib crc32_combine identity), and the
+// contributions are XOR-ed together.
+// ------------------------------------------------------------------------------------------------
+struct CrcParams {
+    const unsigned char* data; uint64_t nbytes; uint64_t seg_len;   // seg_len: multiple of 16
+    const uint32_t* tables;      // [8][256] slicing tables
+    const uint32_t* x2n;         // [64] x^(2^k) mod P, reflected representation
+    uint32_t* out;               // XOR accumulator, zeroed by the caller
+};
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+#pragma unroll 4
+    for (int i = 31; i >= 0; i--) {
+        if (a & (1u << i)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t crc_step8(const uint32_t (*T)[256], uint32_t crc, uint32_t a, uint32_t b) {
+    a ^= crc;
+    return T[7][a & 0xff] ^ T[6][(a >> 8) & 0xff] ^ T[5][(a >> 16) & 0xff] ^ T[4][a >> 24] ^
+           T[3][b & 0xff] ^ T[2][(b >> 8) & 0xff] ^ T[1][(b >> 16) & 0xff] ^ T[0][b >> 24];
+}
+#ifdef MVF_ENGINE_TU
+__global__ void __launch_bounds__(256) crc32_resident(const CrcParams p) {
+    __shared__ uint32_t T[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&T[0][0])[i] = p.tables[i];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t off = t * p.seg_len;
+    uint32_t contrib = 0;
+    if (off < p.nbytes) {
+        const uint64_t len = min(p.seg_len, p.nbytes - off);
+        const unsigned char* s = p.data + off;
+        uint32_t crc = 0xffffffffu;
+        uint64_t i = 0;
+        for (; i + 128 <= len; i += 128) {                  // one 128-byte line per iteration, 8 loads in flight
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = *reinterpret_cast<const uint4*>(s + i + 16 * j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { crc = crc_step8(T, crc, v[j].x, v[j].y); crc = crc_step8(T, crc, v[j].z, v[j].w); }
+        }
+        for (; i + 16 <= len; i += 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s + i);
+            crc = crc_step8(T, crc, v.x, v.y); crc = crc_step8(T, crc, v.z, v.w);
+        }
+        for (; i < len; i++) crc = T[0][(crc ^ s[i]) & 0xff] ^ (crc >> 8);
+        crc = ~crc;
+        // weight x^(8 * bytes after this segment)
+        uint64_t e = 8 * (p.nbytes - off - len);
+        uint32_t w = 0x80000000u;                            // x^0
+        for (int kbit = 0; e; e >>= 1, kbit++) if (e & 1) w = gf2_mulmod(p.x2n[kbit], w);
+        contrib = gf2_mulmod(w, crc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib ^= __shfl_xor_sync(0xffffffffu, contrib, o);
+    if ((threadIdx.x & 31) == 0 && contrib) atomicXor(p.out, contrib);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// gather_rows -- the resident rows of a list of ids (the `vector` field of ScoredVector,
+// examples/similarity_search.rs:18; VectorSpace::get_vectors_batch, src/vectors/vector_space.rs:230-243),
+// raw or widened to f32 like Vector::as_f32.  One warp per id, 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+template <int DT, bool AS_F32>
+__global__ void __launch_bounds__(256) gather_rows(const unsigned char* rows, uint32_t pitch, uint32_t d, uint64_t n,
+                                                    uint64_t row_base, const uint64_t* ids, uint32_t count, unsigned char* out) {
+    constexpr int EPC = Traits<DT>::EPC;
+    constexpr int ES = 16 / EPC;
+    const int lane = threadIdx.x & 31;
+    const uint32_t C = pitch >> 4;
+    for (uint32_t i = blockIdx.x * 8 + (threadIdx.x >> 5); i < count; i += gridDim.x * 8) {
+        const uint64_t gid = ids[i];
+        const bool ok = gid >= row_base && gid - row_base < n;          // ids outside this shard (or invalid) give zero rows
+        const unsigned char* rp = rows + (ok ? gid - row_base : 0) * pitch;
+        for (uint32_t ci = lane; ci < C; ci += 32) {
+            uint4 x = ok ? *reinterpret_cast<const uint4*>(rp + (size_t)ci * 16) : make_uint4(0, 0, 0, 0);
+            if (AS_F32) {
+                float xf[EPC];
+                widen<DT>(x, xf);
+                float* o = reinterpret_cast<float*>(out) + (size_t)i * d + (size_t)ci * EPC;
+#pragma unroll
+                for (int e = 0; e < EPC; e++) if (ci * EPC + e < d) o[e] = xf[e];
+            } else {
+                unsigned char* o = out + (size_t)i * d * ES + (size_t)ci * 16;
+                const unsigned char* xb = reinterpret_cast<const unsigned char*>(&x);
+#pragma unroll
+                for (int e = 0; e < 16; e++) if ((size_t)ci * 16 + e < (size_t)d * ES) o[e] = xb[e];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // synth_fill -- one thread per 16-byte chunk of the (zero-padded) resident layout
 // ------------------------------------------------------------------------------------------------
 template <int DT>

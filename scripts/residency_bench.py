@@ -37,12 +37,14 @@ for no_reg in ("", "1", "1"):
     gs = eng.upload(r.vector_space("embeddings"))
     t4 = time.time()
     st = gs.upload_stats()
+    crc, crc_ms = gs.checksum()
+    gs.verify_checksum(r.vector_space("embeddings"))
     got = gs.search(q, 10)
     same = bool(np.array_equal(got[0], ref[0]) and np.array_equal(got[1].view(np.uint32), ref[1].view(np.uint32)))
     rows_ok = bool(np.array_equal(gs.read_rows(n - 3, 3), rows[-3:]))
     out["uploads"].append({"path": {1: "cudaHostRegister(read-only mapping)", 2: "pinned staging"}[st["path"]],
                            "seconds": st["seconds"], "gb_per_s": st["bytes"] / 1e9 / st["seconds"], "wall_s": t4 - t3,
-                           "search_identical_to_generated_space": same, "tail_rows_identical": rows_ok, "note": st["note"]})
+                           "search_identical_to_generated_space": same, "tail_rows_identical": rows_ok, "note": st["note"], "device_crc32_ms": crc_ms, "device_crc32_gb_per_s": st["bytes"] / 1e9 / (crc_ms * 1e-3)})
     gs.free()
     r.close()
 os.remove(path)

@@ -240,6 +240,58 @@ def test_device_generator_matches_host_generator(engine):
             gs.free()
 
 
+def test_get_vectors_returns_the_rows_behind_a_result(engine):
+    # ScoredVector.vector (examples/similarity_search.rs:18): the rows of the top-k, from the HBM copy
+    for dtype, d in ((oracle.F32, 100), (oracle.F16, 768), (oracle.U8, 13), (oracle.I8, 128)):
+        db = mv.synth_fill_host(dtype, 71, 0, 3000, d)
+        gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+        ids, _, _ = gs.search(as_query(dtype, db[5]), 7)
+        rows = gs.get_vectors(ids[0])
+        assert np.array_equal(rows.view(np.uint8), db[ids[0].astype(np.int64)].view(np.uint8))
+        if dtype in (oracle.F32, oracle.F16):
+            assert np.array_equal(gs.get_vectors(ids[0], as_f32=True), db[ids[0].astype(np.int64)].astype(np.float32))
+        else:
+            with pytest.raises(mv.Build):
+                gs.get_vectors(ids[0], as_f32=True)
+        pad = gs.get_vectors(np.array([2999, 3000, 0xFFFFFFFFFFFFFFFF], dtype=np.uint64))
+        assert np.array_equal(pad[0], db[2999]) and not pad[1:].any()
+        gs.free()
+
+
+def test_device_crc32_matches_zlib_and_the_block_manifest(engine, tmp_path):
+    import zlib
+    # the finished intent of validate_with_checksum (src/reader.rs:172-221), on the resident copy
+    for dtype, n, d in ((oracle.U8, 1, 16), (oracle.U8, 7, 16), (oracle.F32, 1000, 4), (oracle.F16, 4097, 200), (oracle.I8, 300_001, 48),
+                        (oracle.F32, 20_000, 768)):
+        db = mv.synth_fill_host(dtype, 81, 0, n, d)
+        gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+        crc, ms = gs.checksum()
+        assert crc == (zlib.crc32(db.tobytes()) & 0xFFFFFFFF), (dtype, n, d)
+        gs.free()
+    with pytest.raises(mv.Build):                                   # ragged rows are padded in HBM: host check only
+        engine.from_host(mv.synth_fill_host(oracle.U8, 1, 0, 10, 13), mv.DataType.UInt8, mv.DistanceMetric.L2).checksum()
+    rows = mv.synth_fill_host(oracle.F32, 82, 0, 5000, 64)
+    b = mv.MvfBuilder()
+    b.add_vector_space("v", 64, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors_raw("v", rows)
+    good = str(tmp_path / "good.mvf")
+    b.save(good)
+    r = mv.MvfReader.open(good)
+    sp = r.vector_space("v")
+    gs = engine.upload(sp)
+    gs.verify_checksum(sp)
+    raw = bytearray(open(good, "rb").read())
+    raw[4 + 12345] ^= 0x40                                          # one flipped bit in the vector block
+    bad = str(tmp_path / "bad.mvf")
+    open(bad, "wb").write(bytes(raw))
+    rb = mv.MvfReader.open(bad)
+    spb = rb.vector_space("v")
+    gb = engine.upload(spb)
+    with pytest.raises(mv.CorruptedData) as e:
+        gb.verify_checksum(spb)
+    assert "Block checksum mismatch" in str(e.value)
+
+
 def test_profile_counters(engine):
     gs = engine.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, 20000, 128, seed=1)
     engine.profile(True)
