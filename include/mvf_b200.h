@@ -112,6 +112,10 @@ MVF_API int mvf_space_get_vector_f32(const mvf_space* s, uint64_t index, float* 
 /* VectorSpace::map_vector_range: src/vectors/vector_space.rs:155-188 */
 MVF_API int mvf_space_map_vector_range(const mvf_space* s, uint64_t start, uint64_t count,
                                        const void** ptr, size_t* nbytes);
+/* TombstoneInfo{Bitmap} of the space (schema/core.fbs:34-39, schema/types.fbs:35-39): bit i (LSB first)
+ * set = row i deleted.  bitmap = NULL when the footer has none (the reference's builder never writes one,
+ * src/builder.rs:486). */
+MVF_API int mvf_space_tombstones(const mvf_space* s, const void** bitmap, size_t* nbytes, uint64_t* deleted_count);
 /* rows the reference scan `for i in 0..space.total_vectors()` can actually visit:
  * min(total_vectors, block.size / (dimension*elem_size)) -- see DESIGN.md "f16 total_vectors" */
 MVF_API int mvf_space_scannable_vectors(const mvf_space* s, uint64_t* out);
@@ -135,6 +139,8 @@ MVF_API int mvf_builder_add_vectors_raw(mvf_builder* b, const char* space, const
 /* MvfBuilder::add_metadata_column, src/builder.rs:211-236 (opaque bytes) */
 MVF_API int mvf_builder_add_metadata_column(mvf_builder* b, const char* name, int data_type,
                                             const void* bytes, size_t nbytes);
+/* extension: attach a deletion bitmap to a space (written as TombstoneInfo{Bitmap} + one data block) */
+MVF_API int mvf_builder_set_tombstones(mvf_builder* b, const char* space, const void* bitmap, size_t nbytes);
 /* MvfBuilder::build + BuiltMvf::save, src/builder.rs:241-308,404-411, src/io.rs:41-46.
  * Writes the correct total_vectors for every dtype (the reference halves it for Float16,
  * src/builder.rs:476). */
@@ -168,6 +174,11 @@ MVF_API int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type,
 MVF_API int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t global_n,
                                     uint32_t dimension, uint64_t seed, mvf_gpu_space** out);
 MVF_API void mvf_gpu_space_free(mvf_gpu_space* s);
+/* Deletions and pre-filters (TombstoneInfo{Bitmap}, schema/core.fbs:34-39; metadata pre-filters): bit i (LSB
+ * first, GLOBAL row index) of `bitmap` set = row i is excluded from every later search of this space; applied as
+ * a key mask inside the scan / tensor-core epilogues.  NULL clears.  mvf_gpu_space_upload applies the file's own
+ * tombstone bitmap automatically. */
+MVF_API int mvf_gpu_space_set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits);
 MVF_API int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base,
                                uint64_t* global_n, uint32_t* dimension, int* data_type, int* metric);
 /* how the rows got to HBM: path 1 = cudaHostRegister'd mapping, 2 = pinned staging, 0 = generated */

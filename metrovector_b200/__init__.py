@@ -135,6 +135,9 @@ _SIGS = {
     "mvf_gpu_space_read_norms": [_P, _P, _P],
     "mvf_gpu_search": [_P, _P, _INT, _U32, _U32, _INT, _P, _P, _P],
     "mvf_gpu_search_device": [_P, _P, _INT, _U32, _U32, _INT, _P, _P, _P],
+    "mvf_gpu_space_set_row_mask": [_P, _P, _U64],
+    "mvf_space_tombstones": [_P, _c.POINTER(_P), _c.POINTER(_SZ), _c.POINTER(_U64)],
+    "mvf_builder_set_tombstones": [_P, _c.c_char_p, _P, _SZ],
     "mvf_gpu_space_checksum": [_P, _c.POINTER(_U32), _c.POINTER(_c.c_double)],
     "mvf_gpu_space_verify_checksum": [_P, _P],
     "mvf_gpu_space_get_vectors": [_P, _P, _U32, _INT, _P],
@@ -242,6 +245,15 @@ class VectorSpace:
 
     def scannable_vectors(self):
         return self._get("mvf_space_scannable_vectors", _U64)
+
+    def tombstones(self):
+        """Deletion bitmap of the footer's TombstoneInfo{Bitmap} as a boolean array, or None."""
+        ptr, n, cnt = _P(), _SZ(), _U64()
+        _check(_lib.mvf_space_tombstones(self._h, _c.byref(ptr), _c.byref(n), _c.byref(cnt)))
+        if not ptr.value:
+            return None
+        raw = np.frombuffer(_c.string_at(ptr.value, n.value), dtype=np.uint8)
+        return np.unpackbits(raw, bitorder="little").astype(bool)
 
     def get_vector(self, index):                          # vector_space.rs:101-142
         ptr, n = _P(), _SZ()
@@ -369,6 +381,11 @@ class MvfBuilder:
             return
         _check(_lib.mvf_builder_add_vectors_raw(self._h, space.encode(), a.ctypes.data_as(_P), a.shape[0], a.shape[1]))
 
+    def set_tombstones(self, space, deleted):
+        """deleted: boolean array over the space's rows; written as TombstoneInfo{Bitmap}."""
+        bits = np.packbits(np.asarray(deleted, dtype=bool), bitorder="little").tobytes()
+        _check(_lib.mvf_builder_set_tombstones(self._h, space.encode(), bits, len(bits)))
+
     def add_metadata_column(self, name, data_type, data):
         b = bytes(data)
         _check(_lib.mvf_builder_add_metadata_column(self._h, name.encode(), int(data_type), b, len(b)))
@@ -485,6 +502,14 @@ class GpuSpace:
         sq = np.empty(self.local_n, dtype=np.float32)
         _check(_lib.mvf_gpu_space_read_norms(self._h, norm.ctypes.data_as(_P), sq.ctypes.data_as(_P)))
         return norm, sq
+
+    def set_row_mask(self, excluded):
+        """excluded: boolean array over GLOBAL rows (True = never returned), or None to clear."""
+        if excluded is None:
+            _check(_lib.mvf_gpu_space_set_row_mask(self._h, None, 0))
+            return
+        bits = np.packbits(np.asarray(excluded, dtype=bool), bitorder="little")
+        _check(_lib.mvf_gpu_space_set_row_mask(self._h, bits.ctypes.data_as(_P), len(excluded)))
 
     def checksum(self):
         """CRC-32/IEEE of the resident rows, computed on the device.  Returns (crc, kernel_ms)."""

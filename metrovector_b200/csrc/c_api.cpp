@@ -84,6 +84,15 @@ int mvf_space_get_vector_f32(const mvf_space* s, uint64_t index, float* out, siz
 int mvf_space_map_vector_range(const mvf_space* s, uint64_t start, uint64_t count, const void** ptr, size_t* nbytes) {
     return guard([&] { *ptr = s->vs.map_vector_range(start, count, nbytes); });
 }
+int mvf_space_tombstones(const mvf_space* s, const void** bitmap, size_t* nbytes, uint64_t* deleted_count) {
+    return guard([&] {
+        size_t n = 0;
+        const uint8_t* p = s->vs.tombstone_bitmap(&n);
+        if (bitmap) *bitmap = p;
+        if (nbytes) *nbytes = n;
+        if (deleted_count) *deleted_count = s->vs.deleted_count();
+    });
+}
 int mvf_space_scannable_vectors(const mvf_space* s, uint64_t* out) { return guard([&] { *out = s->vs.scannable_vectors(); }); }
 
 int mvf_builder_new(mvf_builder** out) { return guard([&] { *out = new mvf_builder(); }); }
@@ -104,6 +113,9 @@ int mvf_builder_add_vectors_raw(mvf_builder* b, const char* space, const void* r
 }
 int mvf_builder_add_metadata_column(mvf_builder* b, const char* name, int data_type, const void* bytes, size_t nbytes) {
     return guard([&] { b->b.add_metadata_column(name, (DataType)data_type, bytes, nbytes); });
+}
+int mvf_builder_set_tombstones(mvf_builder* b, const char* space, const void* bitmap, size_t nbytes) {
+    return guard([&] { b->b.set_tombstones(space, bitmap, nbytes); });
 }
 int mvf_builder_save(mvf_builder* b, const char* path) { return guard([&] { b->b.save(path); }); }
 

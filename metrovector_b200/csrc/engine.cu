@@ -117,6 +117,8 @@ struct mvf_gpu_space {
     unsigned char* rows = nullptr;
     float* norm = nullptr;
     float* sq = nullptr;
+    uint32_t* mask = nullptr;  // optional row mask (bit set = row excluded): tombstones / pre-filters
+    uint64_t masked_rows = 0;
     int upload_path = 0;       // 0 none/synthetic, 1 cudaHostRegister'd mapping, 2 pinned staging
     double upload_seconds = 0.0;
     std::string upload_note;   // why the in-place registration was not used, if it was not
@@ -296,7 +298,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
     const float* tc_qconst = nullptr;
     if (mvf::tc::eligible(g->tc, g->path, s->dtype, qdtype, metric, nq, kk, s->local_n, s->d, s->pitch)) {
         mvf::tc::SearchArgs a;
-        a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
+        a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.mask = s->mask; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
         a.dtype = s->dtype; a.metric = metric; a.queries = d_queries; a.nq = nq; a.k = kk; a.dump = false;
         mvf::tc::SearchResult r;
         {
@@ -330,7 +332,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
             int NQ = NQmax;
             while ((uint32_t)NQ > nq - q0) NQ >>= 1;
             k::ScanParams p;
-            p.rows = s->rows; p.norm = s->norm; p.queries = d_queries; p.cand = (u64*)g->cand.p;
+            p.rows = s->rows; p.norm = s->norm; p.mask = s->mask; p.queries = d_queries; p.cand = (u64*)g->cand.p;
             p.n = s->local_n; p.d = s->d; p.pitch = s->pitch; p.k = kk; p.P = P; p.metric = metric; p.qdtype = qdtype; p.q0 = q0;
             uint32_t grid = 0;
             if (s->local_n > 0) launch_scan(g, s, p, NQ, &grid);
@@ -516,10 +518,29 @@ void upload_rows(mvf_gpu_space* s, const unsigned char* src, uint64_t nrows, siz
     s->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Row mask: bit i (LSB first) of `bitmap`, indexed by GLOBAL row, set = row i never appears in a result.
+// The shard's bits are re-based to local rows on the host and kept as 32-bit words on the device.
+void set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
+    mvf_gpu* g = s->g;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    if (!bitmap || nbits == 0) { cudaFree(s->mask); s->mask = nullptr; s->masked_rows = 0; return; }
+    const size_t words = (size_t)((s->local_n + k::kPadRows + 31) / 32);
+    std::vector<uint32_t> local(words, 0);
+    uint64_t masked = 0;
+    for (uint64_t i = 0; i < s->local_n; i++) {
+        const uint64_t gbit = s->row_base + i;
+        if (gbit < nbits && ((bitmap[gbit >> 3] >> (gbit & 7)) & 1)) { local[i >> 5] |= 1u << (i & 31); masked++; }
+    }
+    if (!s->mask) CUDA_CHECK(cudaMalloc((void**)&s->mask, words * 4));
+    CUDA_CHECK(cudaMemcpy(s->mask, local.data(), words * 4, cudaMemcpyHostToDevice));
+    s->masked_rows = masked;
+}
+
 void free_space(mvf_gpu_space* s) {
     if (!s) return;
     cudaSetDevice(s->g->device);
-    cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq);
+    cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask);
     delete s;
 }
 
@@ -636,6 +657,9 @@ int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* sp, mvf_gpu_space** out) {
                 upload_rows(s, base, count, (size_t)vs.dimension() * es, !std::getenv("MVF_NO_HOST_REGISTER"));
                 compute_norms(s);
                 CUDA_CHECK(cudaStreamSynchronize(g->stream));
+                // TombstoneInfo{Bitmap} in the footer (schema/core.fbs:34-39): deleted rows never compete
+                size_t tb = 0;
+                if (const uint8_t* tomb = vs.tombstone_bitmap(&tb)) set_row_mask(s, tomb, (uint64_t)tb * 8);
             }
         } catch (...) { free_space(s); throw; }
         *out = s;
@@ -685,6 +709,10 @@ int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t glob
 }
 
 void mvf_gpu_space_free(mvf_gpu_space* s) { free_space(s); }
+
+int mvf_gpu_space_set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
+    return guard([&] { set_row_mask(s, bitmap, nbits); });
+}
 
 int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base, uint64_t* global_n,
                        uint32_t* dimension, int* data_type, int* metric) {
@@ -895,7 +923,7 @@ int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint
         g->queries.reserve(std::max<size_t>(qbytes, 16));
         CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
         mvf::tc::SearchArgs a;
-        a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
+        a.rows = s->rows; a.norm = s->norm; a.sq = s->sq; a.mask = s->mask; a.n = s->local_n; a.d = s->d; a.pitch = s->pitch;
         a.dtype = s->dtype; a.metric = metric; a.queries = g->queries.p; a.nq = nq; a.k = k; a.dump = true;
         mvf::tc::SearchResult r = mvf::tc::run(g->tc, a, g->stream, g->sm_count);
         const uint32_t rows = ((nq + mvf::tc::BM - 1) / mvf::tc::BM) * mvf::tc::BM;

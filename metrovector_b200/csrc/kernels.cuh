@@ -119,6 +119,7 @@ __device__ __forceinline__ void block_bitonic_sort(u64* a, int P, int tid, int n
 struct ScanParams {
     const unsigned char* rows;   // resident shard, row pitch `pitch` bytes (multiple of 16, zero padded)
     const float* norm;           // sqrt(sum x^2) per row (cosine)
+    const uint32_t* mask;        // optional row mask, bit (row & 31) of word row >> 5 set = row excluded (tombstones / filters)
     const void* queries;         // nq_total x d, dtype qdtype, device
     u64* cand;                   // [nq_launch][gridDim.x][k] sorted per-CTA lists
     uint64_t n;                  // rows in the shard

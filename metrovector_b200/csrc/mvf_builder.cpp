@@ -145,6 +145,11 @@ void MvfBuilder::add_metadata_column(const std::string& name, DataType dt, const
     columns_.push_back(std::move(c));
 }
 
+void MvfBuilder::set_tombstones(const std::string& space, const void* bitmap, size_t nbytes) {
+    VectorSpaceBuilder& s = find(space);
+    s.tombstones.assign((const uint8_t*)bitmap, (const uint8_t*)bitmap + nbytes);
+}
+
 std::vector<uint8_t> MvfBuilder::to_bytes() const {
     std::vector<uint8_t> out = {'M', 'V', 'F', '1'};
     std::vector<uint8_t> manifest;
@@ -157,6 +162,13 @@ std::vector<uint8_t> MvfBuilder::to_bytes() const {
     };
     for (const auto& s : spaces_) add_block(s.vectors);
     for (const auto& c : columns_) add_block(c.data);
+    // deletion bitmaps go after the metadata columns (the reference never emits any, so the position is ours)
+    std::vector<uint32_t> tomb_block(spaces_.size(), 0);
+    {
+        uint32_t next = (uint32_t)(spaces_.size() + columns_.size());
+        for (size_t i = 0; i < spaces_.size(); i++)
+            if (!spaces_[i].tombstones.empty()) { add_block(spaces_[i].tombstones); tomb_block[i] = next++; }
+    }
 
     FbEncoder fb;
     std::vector<size_t> space_offs;
@@ -167,8 +179,19 @@ std::vector<uint8_t> MvfBuilder::to_bytes() const {
         size_t flat = fb.end();   // FlatIndex {} (builder.rs:465-468)
         size_t es = element_size(s.data_type);
         uint64_t total = (s.dimension && es) ? s.vectors.size() / ((uint64_t)s.dimension * es) : 0;
+        size_t tomb = 0;
+        if (tomb_block[i]) {
+            uint64_t deleted = 0;
+            for (uint8_t byte : s.tombstones) deleted += (uint64_t)__builtin_popcount(byte);
+            fb.start(3);
+            fb.slot<uint64_t>(2, deleted, 0);
+            fb.slot<uint32_t>(1, tomb_block[i], 0);
+            fb.slot<uint8_t>(0, 1, 0);                        // TombstoneFormat::Bitmap
+            tomb = fb.end();
+        }
         fb.start(12);
         fb.slot<uint64_t>(2, total, 0);
+        fb.slot_off(11, tomb);
         fb.slot_off(8, flat);
         fb.slot<uint32_t>(6, (uint32_t)i, 0);
         fb.slot<uint32_t>(1, s.dimension, 0);

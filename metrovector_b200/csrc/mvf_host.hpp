@@ -79,6 +79,10 @@ struct SpaceInfo {
     DataType data_type = DataType::Float32;
     uint32_t vectors_block_index = 0;
     uint32_t vector_ids_block_index = 0;
+    // table TombstoneInfo, schema/core.fbs:34-39 (never written by the reference's builder, src/builder.rs:486)
+    uint8_t tombstone_format = 0;          // TombstoneFormat: None=0, Bitmap=1, SortedList=2 (schema/types.fbs:35-39)
+    uint32_t tombstone_block_index = 0;    // 0 = no deletions
+    uint64_t deleted_count = 0;
 };
 
 class MvfReader;
@@ -117,6 +121,9 @@ public:
     VectorSpace clone_concurrent() const { return *this; }   // :194-201
     // rows the reference's `for i in 0..total_vectors()` loop can visit before get_vector errors
     uint64_t scannable_vectors() const;
+    // deletion bitmap (bit i, LSB first, = row i deleted) if the footer carries TombstoneInfo{Bitmap}; nullptr otherwise
+    const uint8_t* tombstone_bitmap(size_t* nbytes) const;
+    uint64_t deleted_count() const;
     const MvfReader* reader() const { return reader_; }
 private:
     const SpaceInfo& info() const;
@@ -172,6 +179,7 @@ struct VectorSpaceBuilder {      // src/builder.rs:64-76
     DistanceMetric distance_metric = DistanceMetric::L2;
     DataType data_type = DataType::Float32;
     std::vector<uint8_t> vectors;
+    std::vector<uint8_t> tombstones;       // deletion bitmap, empty = none (extension: the reference never writes one)
 };
 
 class MvfBuilder {               // src/builder.rs:93-98
@@ -181,6 +189,7 @@ public:
     void add_vectors(const std::string& space, const float* rows, size_t nrows, uint32_t dimension);   // :151-196
     void add_vectors_raw(const std::string& space, const void* rows, size_t nrows, uint32_t dimension);
     void add_metadata_column(const std::string& name, DataType dt, const void* bytes, size_t n);       // :211-236
+    void set_tombstones(const std::string& space, const void* bitmap, size_t nbytes);   // TombstoneInfo{Bitmap}, schema/core.fbs:34-39
     std::vector<uint8_t> to_bytes() const;      // build() + BuiltMvf::to_bytes, :241-308,417-558
     void save(const std::string& path) const;   // BuiltMvf::save + MvfWriter::write, io.rs:41-46
 private:

@@ -188,6 +188,12 @@ void MvfReader::parse_footer(const uint8_t* footer, size_t len) {
         s.data_type = (DataType)t.scalar<uint8_t>(5, 0);
         s.vectors_block_index = t.scalar<uint32_t>(6, 0);
         s.vector_ids_block_index = t.scalar<uint32_t>(9, 0);
+        if (size_t tomb = t.indirect(11)) {                       // TombstoneInfo, schema/core.fbs:34-39
+            Table tt(&b, tomb + 0);
+            s.tombstone_format = tt.scalar<uint8_t>(0, 0);
+            s.tombstone_block_index = tt.scalar<uint32_t>(1, 0);
+            s.deleted_count = tt.scalar<uint64_t>(2, 0);
+        }
     }
     has_metadata_ = md != 0;
     if (md) {
@@ -332,6 +338,23 @@ uint64_t VectorSpace::scannable_vectors() const {
     if (vsize == 0) return 0;
     uint64_t fit = blen / vsize;
     return total_vectors() < fit ? total_vectors() : fit;
+}
+
+uint64_t VectorSpace::deleted_count() const { return info().deleted_count; }
+
+const uint8_t* VectorSpace::tombstone_bitmap(size_t* nbytes) const {
+    *nbytes = 0;
+    const SpaceInfo& si = info();
+    if (si.tombstone_format != 1 || si.tombstone_block_index == 0) return nullptr;
+    const auto& blocks = reader_->blocks();
+    if (si.tombstone_block_index >= blocks.size()) throw MvfError::corrupted_data("Invalid tombstone block index");
+    const DataBlock& blk = blocks[si.tombstone_block_index];
+    uint64_t start = 4 + blk.offset;
+    if (start > reader_->file_size() || blk.size > reader_->file_size() - start)
+        throw MvfError::corrupted_data("Block extends beyond file: offset=" + std::to_string(blk.offset) + ", size=" +
+                                       std::to_string(blk.size) + ", file_size=" + std::to_string(reader_->file_size()));
+    *nbytes = (size_t)blk.size;
+    return reader_->data() + start;
 }
 
 // ---- Vector ------------------------------------------------------------------------------------

@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
         }
         // transposed reductions: one row total per lane, then one finalize per lane
         const uint32_t row = g * R + myrow;
-        const bool mine = reporter && row < n;
+        bool mine = reporter && row < n;
+        if (p.mask != nullptr && mine) mine = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;   // deleted / filtered rows never compete
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             float fv = 0.0f; int iv = 0;
@@ -409,7 +410,9 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
             for (int c = 0; c < CNT; c++) {
                 const uint32_t row = g * RPS + (uint32_t)(myr + c) * RPW + ri;
                 u64 pk = kInf;
-                if (reporter && row < n) {
+                bool live = reporter && row < n;
+                if (p.mask != nullptr && live) live = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;
+                if (live) {
                     if (!F && OP == OP_L2) pk = ((u64)ordered_i32(qc[q].qq + iacc[q][c]) << 32) | row;
                     else pk = finalize<DT>(p.metric, facc[q][c], iacc[q][c], 0, qc[q], xn[c], row);
                 }

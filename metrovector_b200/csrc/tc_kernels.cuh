@@ -46,6 +46,7 @@ constexpr int MAX_CAP = 512;       // candidate buffer entries per query (power 
 struct TcParams {
     const float* norm;             // sqrt(sum x^2) per resident row
     const float* sq;               // sum x^2 per row (f32, or int32 bits for integer spaces)
+    const uint32_t* mask;          // optional row mask (bit set = excluded), same layout as ScanParams::mask
     u64* cand;                     // [gridDim.x][EPI_GROUPS][BM][cap] scratch candidate buffers
     u64* out_lists;                // [nq][chunks*EPI_GROUPS][k] sorted lists (key = ordered ranking value, id = local row)
     float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
@@ -200,6 +201,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [2][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 2 * BN);                   // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    uint32_t* valid_s = tmem_slot + 4;                                                    // [2][BN / 32] live-column words
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES);
@@ -290,10 +292,14 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
         u64* const cta_cand = p.cand + ((size_t)blockIdx.x * EPI_GROUPS + grp) * BM * p.cap;
         u64* mybuf = cta_cand + (size_t)qrow * p.cap;
-        // this tile's per-column parameter, loaded one tile ahead (1 column per thread)
-        auto load_param = [&](uint32_t t) -> float {
+        // this tile's per-column parameter, loaded one tile ahead (1 column per thread), and whether the
+        // column is a live row (inside the database, not deleted / filtered out)
+        auto load_param = [&](uint32_t t, bool* live) -> float {
             const uint64_t row = (uint64_t)t * BN + etid;
-            if (row >= p.n) return INT ? __int_as_float(0) : __int_as_float(0x7fc00000);
+            bool ok = row < p.n;
+            if (ok && p.mask != nullptr) ok = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;
+            *live = ok;
+            if (!ok) return __int_as_float(0);
             if (MODE == 0) return p.sq[row];                              // |x|^2 (int32 bits for integer spaces)
             if (INT) return __int_as_float(0);
             if (p.metric == k::M_COS) { const float nm = p.norm[row]; return nm > 0.f ? -1.0f / nm : 0.0f; }
@@ -311,7 +317,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             int thr_i = 0x7fffffff;
             {
                 float* pr = prm + acc * BN;
-                pr[etid] = load_param(t0);
+                bool live0;
+                pr[etid] = load_param(t0, &live0);
+                const unsigned vw0 = __ballot_sync(0xffffffffu, live0);
+                if (lane == 0) valid_s[acc * (BN / 32) + (warp - 2)] = vw0;
                 const uint32_t g0 = __ldcg(p.gthr + q);
                 if (g0 < thr_key) {
                     thr_key = g0;
@@ -322,14 +331,15 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             for (uint32_t t = t0; t < t1; t++) {
                 const float* pr = prm + acc * BN;
                 float nx0 = 0.f;
-                if (t + 1 < t1) nx0 = load_param(t + 1);
+                unsigned nvw = 0;
+                if (t + 1 < t1) { bool lv; nx0 = load_param(t + 1, &lv); nvw = __ballot_sync(0xffffffffu, lv); }
+                const uint32_t* vs = valid_s + acc * (BN / 32) + grp * (EPI_COLS / 32);
                 // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen.
                 // The word is read from L2 now and applied after this tile, so its latency is hidden.
                 const uint32_t gk = __ldcg(p.gthr + q);
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * EPI_COLS;
-                const int64_t left0 = (int64_t)p.n - (int64_t)t * BN - grp * EPI_COLS;  // valid columns from this half's start
                 for (int c2 = 0; c2 < EPI_COLS / (32 * LDG); c2++) {
                     // LDG 32-column TMEM loads per wait (2 halves the exposed tcgen05.ld latency per tile)
                     uint32_t vv[LDG][32];
@@ -363,8 +373,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             }
                         }
                     }
-                    const int64_t left = left0 - cc * 32;               // columns of this 32-group inside the database
-                    if (left < 32) mask &= left <= 0 ? 0u : ((1u << (int)left) - 1u);
+                    mask &= vs[cc];                                      // rows past the end, deleted or filtered out
                     if (p.dump) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
@@ -415,6 +424,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 if (t + 1 < t1) {                                          // publish the next tile's parameters
                     float* prn = prm + acc * BN;
                     prn[etid] = nx0;
+                    if (lane == 0) valid_s[acc * (BN / 32) + (warp - 2)] = nvw;
                 }
                 epi_bar_sync();
             }

@@ -48,7 +48,7 @@ struct TcState {
 };
 
 struct SearchArgs {
-    const unsigned char* rows; const float* norm; const float* sq;
+    const unsigned char* rows; const float* norm; const float* sq; const uint32_t* mask;
     uint64_t n; uint32_t d, pitch; int dtype, metric;
     const void* queries; uint32_t nq, k;
     bool dump;                     // tests: also write the raw ranking values
@@ -72,7 +72,7 @@ inline void init(TcState& st) {
 inline int stages_for_cap(uint32_t cap) { return cap > 256 ? 3 : 4; }   // the sort scratch of k > 64 costs one operand stage
 inline size_t smem_bytes(uint32_t cap) {
     return 1024 + (size_t)stages_for_cap(cap) * STAGE_BYTES + (EPI_THREADS / 32) * (size_t)cap * 8 + 2 * BN * 4 +
-           (2 * MAX_STAGES + 4) * 8 + 16;
+           (2 * MAX_STAGES + 4) * 8 + 16 + 2 * (BN / 32) * 4 + 16;
 }
 inline uint32_t cap_for_k(uint32_t k) {
     static const int big = std::getenv("MVF_TC_BIGCAP") ? std::atoi(std::getenv("MVF_TC_BIGCAP")) : 0;
@@ -164,7 +164,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     make_map(st, &map_x, a.rows, a.dtype, a.n, a.d, a.pitch, BN / CL);
 
     TcParams p;
-    p.norm = a.norm; p.sq = a.sq; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
+    p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
     p.kblocks = (a.d * es + BKB - 1) / BKB;

@@ -155,6 +155,14 @@ def build_mvf(spaces, metadata_columns=(), string_heap=b"", format_version=1,
         blocks.append(_data_block(off, len(d), 0, 0, zlib.crc32(d) & 0xFFFFFFFF))
         payload += d
         off += len(d)
+    tomb_block = {}
+    for i, sp in enumerate(spaces):      # deletion bitmaps after the metadata columns (position is ours: the reference writes none)
+        tb = sp.get("tombstones")
+        if tb:
+            blocks.append(_data_block(off, len(tb), 0, 0, zlib.crc32(tb) & 0xFFFFFFFF))
+            payload += tb
+            off += len(tb)
+            tomb_block[i] = len(blocks) - 1
     heap_index = 0
     if string_heap:
         blocks.append(_data_block(off, len(string_heap), 0, 0, zlib.crc32(string_heap) & 0xFFFFFFFF))
@@ -172,8 +180,17 @@ def build_mvf(spaces, metadata_columns=(), string_heap=b"", format_version=1,
         total = sp.get("total_vectors")
         if total is None:
             total = (len(sp["data"]) // (dim * es)) if dim else 0
+        tomb = None
+        if i in tomb_block:
+            deleted = sum(bin(x).count("1") for x in sp["tombstones"])
+            b.start_table(3)
+            b.slot_scalar(2, "Q", deleted, 0)
+            b.slot_scalar(1, "I", tomb_block[i], 0)
+            b.slot_scalar(0, "B", 1, 0)            # TombstoneFormat::Bitmap
+            tomb = b.end_table()
         b.start_table(12)
         b.slot_scalar(2, "Q", total, 0)
+        b.slot_offset(11, tomb)
         b.slot_scalar(9, "I", 0, 0)
         b.slot_offset(8, flat)
         b.slot_scalar(6, "I", i, 0)
@@ -277,7 +294,13 @@ def parse_mvf(data):
         for i in range(ns):
             p = vs + 4 + 4 * i
             t = _Table(footer, p + struct.unpack_from("<I", footer, p)[0])
+            tomb = t.indirect(11)
+            tinfo = None
+            if tomb is not None:
+                tt = _Table(footer, tomb)
+                tinfo = dict(format=tt.scalar(0, "B", 0), data_block_index=tt.scalar(1, "I", 0), deleted_count=tt.scalar(2, "Q", 0))
             out["spaces"].append(dict(
+                tombstones=tinfo,
                 name=t.string(0), dimension=t.scalar(1, "I", 0), total_vectors=t.scalar(2, "Q", 0),
                 vector_type=t.scalar(3, "B", 0), distance_metric=t.scalar(4, "B", 0),
                 data_type=t.scalar(5, "B", 0), vectors_block_index=t.scalar(6, "I", 0),

@@ -1,3 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "crc32 or get_vectors" 2>&1 | tail -15
-MVF_UPLOAD_THREADS=8 timeout 600 python scripts/residency_bench.py
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py -x -q 2>&1 | tail -15

@@ -292,6 +292,65 @@ def test_device_crc32_matches_zlib_and_the_block_manifest(engine, tmp_path):
     assert "Block checksum mismatch" in str(e.value)
 
 
+def _masked_oracle(db, dtype, metric, q, k, excluded):
+    keep = np.flatnonzero(~excluded)
+    ids, sc, isc = oracle.topk(db[keep], dtype, metric, q, k)
+    return keep[ids.astype(np.int64)], sc, isc
+
+
+@pytest.mark.parametrize("dtype,d,n", [(oracle.F32, 768, 4000), (oracle.U8, 128, 30000), (oracle.F16, 96, 9000), (oracle.I8, 16, 5000)])
+def test_row_mask_excludes_rows_on_both_paths(engine, dtype, d, n):
+    # tombstones / pre-filters as a key mask: masked rows never appear
+    rng = np.random.default_rng(3)
+    db = mv.synth_fill_host(dtype, 95, 0, n, d)
+    excluded = rng.random(n) < 0.3
+    gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+    k = 10
+    q = mv.synth_fill_host(dtype, 96, 0, 70, d)
+    q[0] = db[np.flatnonzero(excluded)[0]]                 # a query equal to a deleted row must not find it
+    try:
+        for path in (1, 2):
+            if path == 2 and dtype == oracle.F32:
+                continue
+            engine.set_path(path)
+            qq = q if path == 2 else np.stack([as_query(dtype, r) for r in q[:5]])
+            gs.set_row_mask(excluded)
+            ids, sc, isc = gs.search(qq, k)
+            for qi in (0, 1, 2, len(qq) - 1):
+                query = qq[qi].astype(np.float32) if dtype in (oracle.F32, oracle.F16) else qq[qi]
+                o_ids, o_sc, o_isc = _masked_oracle(db, dtype, oracle.L2, query, k, excluded)
+                assert not excluded[ids[qi].astype(np.int64)].any()
+                if dtype in (oracle.I8, oracle.U8):
+                    assert ids[qi].tolist() == o_ids.tolist() and isc[qi].tolist() == o_isc.tolist()
+                else:
+                    assert ids[qi].tolist() == o_ids.tolist()
+                    assert np.allclose(sc[qi], o_sc, rtol=1e-4, atol=1e-4)
+            gs.set_row_mask(None)                              # cleared: the deleted row is found again
+            ids, _, _ = gs.search(qq[:1], 1)
+            assert ids[0][0] == np.flatnonzero(excluded)[0]
+    finally:
+        engine.set_path(0)
+        gs.free()
+
+
+def test_upload_applies_the_files_tombstones(engine, tmp_path):
+    n, d = 2000, 64
+    rows = mv.synth_fill_host(oracle.F32, 97, 0, n, d)
+    deleted = np.zeros(n, dtype=bool)
+    deleted[::3] = True
+    b = mv.MvfBuilder()
+    b.add_vector_space("v", d, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors_raw("v", rows)
+    b.set_tombstones("v", deleted)
+    path = str(tmp_path / "t.mvf")
+    b.save(path)
+    r = mv.MvfReader.open(path)
+    gs = engine.upload(r.vector_space("v"))
+    ids, sc, _ = gs.search(rows[0], 5)                         # row 0 is deleted
+    o_ids, o_sc, _ = _masked_oracle(rows, oracle.F32, oracle.L2, rows[0], 5, deleted)
+    assert ids[0].tolist() == o_ids.tolist() and ids[0][0] != 0
+
+
 def test_profile_counters(engine):
     gs = engine.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, 20000, 128, seed=1)
     engine.profile(True)

@@ -170,3 +170,46 @@ def test_threaded_baseline_matches_single_scan():
     for faithful in (False, True):
         _, ids2, sc2 = oracle.scan_timed(db, oracle.F32, oracle.L2, q, 10, threads=4, faithful=faithful)
         assert ids2.tolist() == ids.tolist() and np.array_equal(sc2, sc)
+
+
+def test_oracle_bits_equal_a_python_float32_restatement():
+    """Independent restatement of the reference expression in numpy float32 scalars, one rounded op at a
+    time (examples/similarity_search.rs:152-157: t = a - b; s = s + t*t; sqrt): the C oracle must agree
+    bit for bit, which also proves it was built without FMA contraction or reassociation."""
+    f = np.float32
+    rng = np.random.default_rng(11)
+    for dtype in (oracle.F32, oracle.F16):
+        db = oracle.synth(dtype, 91, 0, 40, 51)
+        q = oracle.synth(dtype, 92, 0, 1, 51)[0].astype(np.float32)
+        want = []
+        for i in range(40):
+            x = db[i].astype(np.float32)
+            s = f(0.0)
+            for j in range(51):
+                t = f(q[j] - x[j])
+                s = f(s + f(t * t))
+            want.append(f(np.sqrt(s)))
+        want = np.array(want, dtype=np.float32)
+        order = np.lexsort((np.arange(40), want))
+        ids, sc, _ = oracle.topk(db, dtype, oracle.L2, q, 40)
+        assert ids.tolist() == order.tolist()
+        assert np.array_equal(sc.view(np.uint32), want[order].view(np.uint32))
+        # cosine and dot, same discipline (ours)
+        dots, nx = [], []
+        for i in range(40):
+            x = db[i].astype(np.float32)
+            s = f(0.0); n2 = f(0.0)
+            for j in range(51):
+                s = f(s + f(q[j] * x[j])); n2 = f(n2 + f(x[j] * x[j]))
+            dots.append(s); nx.append(n2)
+        qn = f(0.0)
+        for j in range(51):
+            qn = f(qn + f(q[j] * q[j]))
+        cos = np.array([f(f(1.0) - f(dd / f(f(np.sqrt(qn)) * f(np.sqrt(n2))))) for dd, n2 in zip(dots, nx)], dtype=np.float32)
+        ids, sc, _ = oracle.topk(db, dtype, oracle.COS, q, 40)
+        order = np.lexsort((np.arange(40), cos))
+        assert ids.tolist() == order.tolist() and np.array_equal(sc.view(np.uint32), cos[order].view(np.uint32))
+        ids, sc, _ = oracle.topk(db, dtype, oracle.IP, q, 40)
+        dd = np.array(dots, dtype=np.float32)
+        order = np.lexsort((np.arange(40), -dd))
+        assert ids.tolist() == order.tolist() and np.array_equal(sc.view(np.uint32), dd[order].view(np.uint32))

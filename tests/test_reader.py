@@ -260,3 +260,36 @@ def test_truncated_block_is_corrupted_data(tmp_path):
         r.validate()
     with pytest.raises(mv.CorruptedData):
         r.vector_space("s").get_vector(0)
+
+
+def test_tombstone_bitmap_round_trip(tmp_path):
+    # TombstoneInfo{Bitmap} (schema/core.fbs:34-39, schema/types.fbs:35-39): the reference reserves it and never
+    # writes it (src/builder.rs:486); our writer and reader implement the Bitmap format
+    rows = np.arange(40 * 4, dtype=np.float32).reshape(40, 4)
+    deleted = np.zeros(40, dtype=bool)
+    deleted[[0, 7, 8, 31, 39]] = True
+    b = mv.MvfBuilder()
+    b.add_vector_space("live", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors("live", rows)
+    b.add_vector_space("plain", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors("plain", rows[:3])
+    b.set_tombstones("live", deleted)
+    b.add_metadata_column("ids", mv.DataType.UInt32, struct.pack("<40I", *range(40)))
+    path = str(tmp_path / "tomb.mvf")
+    b.save(path)
+    r = mv.MvfReader.open(path)
+    r.validate_with_checksum()
+    got = r.vector_space("live").tombstones()
+    assert got is not None and np.array_equal(got[:40], deleted) and not got[40:].any()
+    assert r.vector_space("plain").tombstones() is None
+    assert np.array_equal(r.vector_space("live").map_vector_range(0, 40), rows)
+    data = open(path, "rb").read()
+    parsed = fmt.parse_mvf(data)
+    assert parsed["spaces"][0]["tombstones"] == dict(format=1, data_block_index=3, deleted_count=5)
+    assert parsed["spaces"][1]["tombstones"] is None
+    # the independent Python writer produces the same bytes
+    bits = np.packbits(deleted, bitorder="little").tobytes()
+    py = fmt.build_mvf([dict(name="live", dimension=4, vector_type=0, distance_metric=0, data_type=0, data=rows.tobytes(), tombstones=bits),
+                        dict(name="plain", dimension=4, vector_type=0, distance_metric=0, data_type=0, data=rows[:3].tobytes())],
+                       metadata_columns=[dict(name="ids", data_type=4, data=struct.pack("<40I", *range(40)))])
+    assert py == data
