@@ -58,6 +58,7 @@ struct TcParams {
     int metric;                    // k::M_L2 / M_IP / M_COS
     int is_int;                    // 0: f16 operands / f32 accum, 1: int8 operands / s32 accum
     uint32_t idesc;                // tcgen05 instruction descriptor
+    uint32_t l2_prefetch_tiles;    // database tiles the producer prefetches into L2 ahead of its TMA loads (0 = off)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -100,6 +101,9 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -243,6 +247,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
                         const int kc = (int)(kb * (INT ? 128u : 64u));   // element coordinate along K
                         tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
+                        if (p.l2_prefetch_tiles && t + p.l2_prefetch_tiles < t1)   // pull a later tile's rows from HBM into L2 now
+                            tma_prefetch_l2_2d(&map_x, kc, (int)((t + p.l2_prefetch_tiles) * BN + crank * (BN / CL)));
                         if (CL > 1)      // this CTA's share of the database tile, delivered to every CTA of the cluster
                             tma_load_2d_mc(a_dst + A_BYTES + crank * (B_BYTES / CL), &map_x, full0 + 8 * stage, kc,
                                            (int)(t * BN + crank * (BN / CL)), (uint16_t)((1u << CL) - 1));

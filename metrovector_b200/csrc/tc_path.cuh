@@ -41,6 +41,7 @@ struct Buf {
 struct TcState {
     EncodeTiledFn encode = nullptr;
     Buf qprep, qconst, cand, lists, dump, gthr;
+    int l2_prefetch = 0;           // (measured slower: the kernel is power-capped, extra L2 traffic costs clocks) database tiles prefetched into L2 ahead of the TMA loads (MVF_TC_PREFETCH=0..4)
     int ld_group = 1;              // TMEM loads issued per tcgen05.wait::ld in the epilogue (MVF_TC_LDG=1|2)
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
     int min_batch = 64;            // auto path: batches at least this large go to the tensor cores (MVF_TC_MIN_BATCH)
@@ -67,6 +68,7 @@ inline void init(TcState& st) {
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
     if (const char* c = std::getenv("MVF_TC_LDG")) st.ld_group = std::atoi(c) == 2 ? 2 : 1;
+    if (const char* c = std::getenv("MVF_TC_PREFETCH")) st.l2_prefetch = std::max(0, std::min(4, std::atoi(c)));
 }
 
 inline int stages_for_cap(uint32_t cap) { return cap > 256 ? 3 : 4; }   // the sort scratch of k > 64 costs one operand stage
@@ -172,6 +174,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     p.metric = a.metric; p.is_int = is_int ? 1 : 0;
     const uint32_t fmt = a.dtype == k::DT_I8 ? 1u : 0u;     // kind::i8: 0 = unsigned, 1 = signed; kind::f16: 0 = F16
     const uint32_t cfmt = is_int ? 2u : 1u;                  // accumulator: S32 / F32
+    p.l2_prefetch_tiles = (uint32_t)st.l2_prefetch;
     p.idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     if (a.dump) {
         st.dump.reserve((size_t)mtiles * BM * (size_t)ntiles * BN * 4);

@@ -1,7 +1,8 @@
 #!/bin/bash
-# same-box A/B of a tensor-path knob: alternates the two settings so power/thermal state is shared
-VAR=${1:-MVF_TC_LDG}; A=${2:-1}; B=${3:-2}
-for rep in 1 2; do for V in $A $B; do
+# same-box A/B of a tensor-path knob: alternates the settings so power/thermal state is shared
+VAR=${1:-MVF_TC_LDG}; shift
+timeout 300 python -m pytest tests/test_gpu_tc.py -x -q 2>&1 | tail -3
+for rep in 1 2; do for V in "$@"; do
 echo "== $VAR=$V (rep $rep)"
 env $VAR=$V timeout 600 python scripts/bench_summary.py C --steps 6 --warmup 3
 env $VAR=$V timeout 600 python scripts/bench_summary.py D1024 --steps 6 --warmup 3 --rows 20000000
