@@ -573,6 +573,7 @@ int mvf_gpu_init(int device, mvf_gpu** out) {
         g->own_stream = true;
         if (const char* c = std::getenv("MVF_SCAN_CTAS_PER_SM")) g->ctas_per_sm_cap = std::atoi(c);
         if (const char* c = std::getenv("MVF_UPLOAD_THREADS")) g->upload_threads = std::max(1, std::min(16, std::atoi(c)));
+        try { mvf::tc::init(g->tc); } catch (...) { /* the tensor path reports its own error when it is first used */ }
         *out = g;
     });
 }

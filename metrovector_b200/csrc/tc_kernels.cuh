@@ -318,9 +318,23 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
             const uint32_t q = mt * BM + qrow;
             int cnt = 0;
-            uint32_t thr_key = 0xffffffffu;                              // ordered key of the threshold
+            // thr_key: tightest known bound on this query's k-th best key (local list or any CTA's, via gthr);
+            // loc_key: k-th best key of the local list.  Rows arrive in increasing index order, so a row that
+            // only TIES the local k-th can never displace it (strict compare); a tie with a bound that came from
+            // another CTA may still win on the index, so it is kept (<=).  One compare per element either way:
+            // the strict case compares against the next smaller key.
+            uint32_t thr_key = 0xffffffffu, loc_key = 0xffffffffu;
             float thr_f = __int_as_float(0x7f800000);                   // +inf: everything passes until k are known
             int thr_i = 0x7fffffff;
+            auto refresh_threshold = [&]() {
+                if (q >= p.nq) { thr_f = __int_as_float(0xff800000); thr_i = (int)0x80000000; return; }   // padding row of the query tile
+                if (thr_key == 0xffffffffu) { thr_f = __int_as_float(0x7f800000); thr_i = 0x7fffffff; return; }
+                const bool ties = thr_key < loc_key;
+                if (!ties && thr_key == 0) { thr_f = __int_as_float(0xff800000); thr_i = (int)0x80000000; return; }
+                const uint32_t ck = ties ? thr_key : thr_key - 1;
+                if (INT) thr_i = (int)(ck ^ 0x80000000u); else thr_f = k::unordered_f32(ck);
+            };
+            refresh_threshold();
             {
                 float* pr = prm + acc * BN;
                 bool live0;
@@ -328,10 +342,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 const unsigned vw0 = __ballot_sync(0xffffffffu, live0);
                 if (lane == 0) valid_s[acc * (BN / 32) + (warp - 2)] = vw0;
                 const uint32_t g0 = __ldcg(p.gthr + q);
-                if (g0 < thr_key) {
-                    thr_key = g0;
-                    if (INT) thr_i = (int)(g0 ^ 0x80000000u); else thr_f = k::unordered_f32(g0);
-                }
+                if (g0 < thr_key) { thr_key = g0; refresh_threshold(); }
                 epi_bar_sync();
             }
             for (uint32_t t = t0; t < t1; t++) {
@@ -409,10 +420,9 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             cnt = ncnt;
                             if (kth != kInf) {
                                 const uint32_t kk = (uint32_t)(kth >> 32);
-                                if (kk < thr_key) {
-                                    thr_key = kk;
-                                    if (INT) thr_i = (int)(kk ^ 0x80000000u); else thr_f = k::unordered_f32(kk);
-                                }
+                                loc_key = kk;
+                                if (kk < thr_key) thr_key = kk;
+                                refresh_threshold();
                                 atomicMin(p.gthr + q, kk);
                             }
                         }
@@ -422,10 +432,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // all epilogue warps -> accumulator free
-                if (gk < thr_key) {
-                    thr_key = gk;
-                    if (INT) thr_i = (int)(gk ^ 0x80000000u); else thr_f = k::unordered_f32(gk);
-                }
+                if (gk < thr_key) { thr_key = gk; refresh_threshold(); }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 if (t + 1 < t1) {                                          // publish the next tile's parameters
                     float* prn = prm + acc * BN;

@@ -44,7 +44,10 @@ struct TcState {
     int l2_prefetch = 0;           // (measured slower: the kernel is power-capped, extra L2 traffic costs clocks) database tiles prefetched into L2 ahead of the TMA loads (MVF_TC_PREFETCH=0..4)
     int ld_group = 1;              // TMEM loads issued per tcgen05.wait::ld in the epilogue (MVF_TC_LDG=1|2)
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
-    int min_batch = 64;            // auto path: batches at least this large go to the tensor cores (MVF_TC_MIN_BATCH)
+    // auto path: batches at least this large go to the tensor cores.  Measured crossover (scripts/crossover.py):
+    // f16 768-d rows: the scan kernel pays a convert + FMA per element per query and loses from 4 queries on;
+    // uint8 128-d rows: dp4a keeps the scan ahead up to ~7 queries.  MVF_TC_MIN_BATCH overrides both.
+    int min_batch_f16 = 4, min_batch_i8 = 8;
     bool attr_set = false;
 };
 
@@ -65,7 +68,7 @@ inline void init(TcState& st) {
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || !fn) { cudaGetLastError(); throw MvfError::cuda("cuTensorMapEncodeTiled is not available from the driver"); }
     st.encode = (EncodeTiledFn)fn;
-    if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch = std::max(1, std::atoi(c));
+    if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch_f16 = st.min_batch_i8 = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
     if (const char* c = std::getenv("MVF_TC_LDG")) st.ld_group = std::atoi(c) == 2 ? 2 : 1;
     if (const char* c = std::getenv("MVF_TC_PREFETCH")) st.l2_prefetch = std::max(0, std::min(4, std::atoi(c)));
@@ -93,7 +96,7 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
     if (!(f16 || i8)) return false;
     if (k > 128 || n == 0 || d == 0) return false;
     if (path == 2) return true;
-    return nq >= (uint32_t)st.min_batch && n >= 4096;
+    return nq >= (uint32_t)(f16 ? st.min_batch_f16 : st.min_batch_i8) && n >= 4096;
 }
 
 template <bool INT, int MODE, int LDG>

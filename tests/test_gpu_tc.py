@@ -78,3 +78,30 @@ def test_tensor_and_scan_paths_agree(engine):
     finally:
         engine.set_path(0)
         gs.free()
+
+
+def test_ties_and_degenerate_queries_on_the_tensor_path(engine):
+    # all-equal ranking values (zero query under cosine, duplicated rows, 2-valued bytes): exact lowest-index
+    # tie-breaking must survive the threshold logic (strict vs. the local list, non-strict vs. other CTAs' bounds)
+    engine.set_path(2)
+    try:
+        base = mv.synth_fill_host(oracle.F16, 3, 0, 500, 64)
+        db = np.concatenate([base] * 40)                                  # every row appears 40 times
+        gs = engine.from_host(db, mv.DataType.Float16, mv.DistanceMetric.Cosine)
+        q = np.concatenate([np.zeros((1, 64), dtype=np.float16), base[:70]])
+        for metric in (oracle.COS, oracle.L2, oracle.IP):
+            ids, sc, isc = gs.search(q, 50, metric=metric)
+            check_batch(db, oracle.F16, metric, q.astype(np.float32)[:6], 50, ids[:6], sc[:6], isc[:6])
+        ids, sc, _ = gs.search(q[:1], 10, metric=oracle.COS)              # zero query: every distance is 1 -> ids 0..9
+        assert ids[0].tolist() == list(range(10)) and (sc[0] == 1.0).all()
+        gs.free()
+        rng = np.random.default_rng(4)
+        dbu = rng.integers(0, 2, (60000, 128)).astype(np.uint8)
+        gu = engine.from_host(dbu, mv.DataType.UInt8, mv.DistanceMetric.L2)
+        qu = rng.integers(0, 2, (130, 128)).astype(np.uint8)
+        ids, sc, isc = gu.search(qu, 64)
+        check_batch(dbu, oracle.U8, oracle.L2, qu[:4], 64, ids[:4], sc[:4], isc[:4])
+        check_batch(dbu, oracle.U8, oracle.L2, qu[-2:], 64, ids[-2:], sc[-2:], isc[-2:])
+        gu.free()
+    finally:
+        engine.set_path(0)
