@@ -35,13 +35,15 @@ def main():
     solo = mv.GpuEngine(local) if rank == 0 else None
     failures = 0
     cases = [(0, 0, 20000, 128, 10, 3), (1, 2, 30001, 96, 10, 2), (3, 0, 50000, 128, 25, 4), (2, 1, 7, 16, 5, 2),
-             (3, 2, 40000, 64, 10, 1), (0, 1, 1000, 768, 100, 9)]
+             (3, 2, 40000, 64, 10, 1), (0, 1, 1000, 768, 100, 9),
+             # batches that take the tensor-core path on every rank (keys are K2 ranking values until the final merge)
+             (3, 0, 60000, 128, 10, 40), (1, 2, 50000, 128, 10, 70), (1, 0, 50000, 64, 33, 130), (2, 1, 40000, 96, 10, 16)]
     for dtype, metric, n, d, k, nq in cases:
         gs = eng.synthetic(mv.DataType(dtype), mv.DistanceMetric(metric), n, d, seed=321)
         b, c = mv.shard_range(n, world, rank)
         assert (gs.row_base, gs.local_n, gs.global_n) == (b, c, n)
         q = mv.synth_fill_host(dtype, 654, 0, nq, d)
-        queries = np.stack([as_query(dtype, r) for r in q])
+        queries = q if (dtype == 1 and nq >= 4) else np.stack([as_query(dtype, r) for r in q])   # f16 batches stay f16 (tensor path)
         ids, sc, isc = gs.search(queries, k)
         # every rank must hold the same answer
         t = torch.from_numpy(ids.view(np.int64).copy()).cuda()
@@ -50,7 +52,7 @@ def main():
         assert torch.equal(t, ref), "ranks disagree"
         if rank == 0:
             db = mv.synth_fill_host(dtype, 321, 0, n, d)
-            check_batch(db, dtype, metric, queries, k, ids, sc, isc)
+            check_batch(db, dtype, metric, queries.astype(np.float32) if dtype == 1 else queries, k, ids, sc, isc)
             full = solo.from_host(db, mv.DataType(dtype), mv.DistanceMetric(metric))
             ids1, sc1, isc1 = full.search(queries, k)
             same = np.array_equal(ids, ids1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32)) and np.array_equal(isc, isc1)
