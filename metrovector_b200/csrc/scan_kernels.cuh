@@ -208,69 +208,71 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
     // the row end when a tile is consumed; the common shapes skip that work entirely
     auto run = [&](auto ragged_tag) {
     constexpr bool RAGGED = decltype(ragged_tag)::value;
-    while (g < groups) {
+    float facc[NQ][R]; int iacc[NQ][R]; int ixx[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        ixx[r] = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; }
+    }
+    uint32_t c = 0;                          // chunk of the current group the step consumes
+    float xn_n = 0.0f;
+    // One step = one 16-byte chunk of all R rows.  Two register tiles alternate: the step consumes `cur`
+    // while `nxt` is refilled with the following chunk (or the next group's first one), so a load never
+    // lands in registers that still have to be copied somewhere else.
+    auto step = [&](uint4 (&cur)[R], uint4 (&nxt)[R]) {
+        const bool lastc = c + 1 == CPL;
         const uint32_t gn = g + gstride;
         const bool more = gn < groups && gn > g;
-        // the refill is unconditional (a predicated load would force register copies): after the
-        // last group it just re-reads the current one
-        const unsigned char* ptr_n = more ? lane_base + (size_t)gn * R * pitch : ptr;
-        float xn_n = 0.0f;
-        if (p.metric == M_COS && more) xn_n = p.norm[gn * R + myrow];
-        float facc[NQ][R]; int iacc[NQ][R]; int ixx[R];
+        // the refill is unconditional (a predicated load would force register copies): after the very last
+        // chunk it just re-reads the current one
+        const unsigned char* tp = lastc ? (more ? lane_base + (size_t)gn * R * pitch : ptr) : ptr + (size_t)(c + 1) * 512;
+        if (lastc && p.metric == M_COS && more) xn_n = p.norm[gn * R + myrow];
+        const uint32_t ci = c * 32 + lane;
+        // ragged rows: lanes past the row end read whatever follows (always inside the padded buffer) and
+        // the tile is zeroed when consumed
+        const bool dead = RAGGED && ci >= C;
+        float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            if (F) {
+                const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
+                float4 a = reinterpret_cast<const float4*>(qb)[ci];
+                qf[q][0] = a.x; qf[q][1 % EPC] = a.y; qf[q][2 % EPC] = a.z; qf[q][3 % EPC] = a.w;
+                if (EPC == 8) {
+                    float4 b = reinterpret_cast<const float4*>(qb + dpad / 2)[ci];
+                    qf[q][4 % EPC] = b.x; qf[q][5 % EPC] = b.y; qf[q][6 % EPC] = b.z; qf[q][7 % EPC] = b.w;
+                }
+            } else {
+                qv[q] = reinterpret_cast<const uint4*>(q_s + (size_t)q * dpad)[ci];
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            ixx[r] = 0;
+            nxt[r] = ldg_stream16(tp + (size_t)r * pitch);
+            uint4 cv = cur[r];
+            if (RAGGED && dead) cv = make_uint4(0, 0, 0, 0);
+            if (F) {
+                float xf[EPC];
+                widen<DT>(cv, xf);
 #pragma unroll
-            for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; }
-        }
-        for (uint32_t c = 0; c < CPL; c++) {
-            const bool lastc = c + 1 == CPL;
-            const unsigned char* tp = lastc ? ptr_n : ptr + (size_t)(c + 1) * 512;
-            const uint32_t ci = c * 32 + lane;
-            // ragged rows: lanes past the row end read whatever follows (always inside the padded
-            // buffer) and the tile is zeroed when consumed
-            const bool dead = RAGGED && ci >= C;
-            float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                if (F) {
-                    const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
-                    float4 a = reinterpret_cast<const float4*>(qb)[ci];
-                    qf[q][0] = a.x; qf[q][1 % EPC] = a.y; qf[q][2 % EPC] = a.z; qf[q][3 % EPC] = a.w;
-                    if (EPC == 8) {
-                        float4 b = reinterpret_cast<const float4*>(qb + dpad / 2)[ci];
-                        qf[q][4 % EPC] = b.x; qf[q][5 % EPC] = b.y; qf[q][6 % EPC] = b.z; qf[q][7 % EPC] = b.w;
-                    }
-                } else {
-                    qv[q] = reinterpret_cast<const uint4*>(q_s + (size_t)q * dpad)[ci];
+                for (int q = 0; q < NQ; q++) accum_float<DT, OP>(xf, qf[q], facc[q][r]);
+            } else {
+                if (OP == OP_L2) {
+                    ixx[r] = dp4<DT>(cv.x, cv.x, ixx[r]); ixx[r] = dp4<DT>(cv.y, cv.y, ixx[r]);
+                    ixx[r] = dp4<DT>(cv.z, cv.z, ixx[r]); ixx[r] = dp4<DT>(cv.w, cv.w, ixx[r]);
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                uint4 cur = x[r];
-                x[r] = ldg_stream16(tp + (size_t)r * pitch);
-                if (RAGGED && dead) cur = make_uint4(0, 0, 0, 0);
-                if (F) {
-                    float xf[EPC];
-                    widen<DT>(cur, xf);
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) accum_float<DT, OP>(xf, qf[q], facc[q][r]);
-                } else {
-                    if (OP == OP_L2) {
-                        ixx[r] = dp4<DT>(cur.x, cur.x, ixx[r]); ixx[r] = dp4<DT>(cur.y, cur.y, ixx[r]);
-                        ixx[r] = dp4<DT>(cur.z, cur.z, ixx[r]); ixx[r] = dp4<DT>(cur.w, cur.w, ixx[r]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        int a = iacc[q][r];
-                        a = dp4<DT>(qv[q].x, cur.x, a); a = dp4<DT>(qv[q].y, cur.y, a);
-                        a = dp4<DT>(qv[q].z, cur.z, a); a = dp4<DT>(qv[q].w, cur.w, a);
-                        iacc[q][r] = a;
-                    }
+                for (int q = 0; q < NQ; q++) {
+                    int a = iacc[q][r];
+                    a = dp4<DT>(qv[q].x, cv.x, a); a = dp4<DT>(qv[q].y, cv.y, a);
+                    a = dp4<DT>(qv[q].z, cv.z, a); a = dp4<DT>(qv[q].w, cv.w, a);
+                    iacc[q][r] = a;
                 }
             }
         }
-        // transposed reductions: one row total per lane, then one finalize per lane
+        if (!lastc) { c++; return; }
+        // end of the row group -- transposed reductions: one row total per lane, then one finalize per lane
         const uint32_t row = g * R + myrow;
         bool mine = reporter && row < n;
         if (p.mask != nullptr && mine) mine = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;   // deleted / filtered rows never compete
@@ -292,7 +294,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
             }
             offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane);
         }
-        g = more ? gn : groups; ptr = ptr_n; xn = xn_n;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            ixx[r] = 0;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; }
+        }
+        c = 0; g = more ? gn : groups; ptr = tp; xn = xn_n;
+    };
+    uint4 y[R];                              // the second register tile
+    while (g < groups) {
+        step(x, y);
+        if (g >= groups) break;
+        step(y, x);
     }
     };
     if (ragged) run(std::true_type{}); else run(std::false_type{});
@@ -364,7 +378,8 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
             }
         }
     }
-    while (g < groups) {
+    // one step = one row group; two register tiles alternate like in the wide kernel
+    auto step = [&](uint4 (&cur)[R], uint4 (&nxt)[R]) {
         const uint32_t gn = g + gstride;
         const bool more = gn < groups && gn > g;
         const unsigned char* ptr_n = lane_base + (size_t)(more ? gn : g) * RPS * pitch;   // unconditional refill
@@ -380,25 +395,25 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
         float facc[NQ][R]; int iacc[NQ][R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            uint4 cur = x[r];
-            x[r] = ldg_stream16(ptr_n + (size_t)r * step_pitch);
-            if (!active) cur = make_uint4(0, 0, 0, 0);
+            nxt[r] = ldg_stream16(ptr_n + (size_t)r * step_pitch);
+            uint4 cv = cur[r];
+            if (!active) cv = make_uint4(0, 0, 0, 0);
             if (F) {
                 float xf[EPC];
-                widen<DT>(cur, xf);
+                widen<DT>(cv, xf);
 #pragma unroll
                 for (int q = 0; q < NQ; q++) { facc[q][r] = 0.0f; iacc[q][r] = 0; accum_float<DT, OP>(xf, qf[q], facc[q][r]); }
             } else {
                 int xx = 0;
                 if (OP == OP_L2) {
-                    xx = dp4<DT>(cur.x, cur.x, xx); xx = dp4<DT>(cur.y, cur.y, xx);
-                    xx = dp4<DT>(cur.z, cur.z, xx); xx = dp4<DT>(cur.w, cur.w, xx);
+                    xx = dp4<DT>(cv.x, cv.x, xx); xx = dp4<DT>(cv.y, cv.y, xx);
+                    xx = dp4<DT>(cv.z, cv.z, xx); xx = dp4<DT>(cv.w, cv.w, xx);
                 }
 #pragma unroll
                 for (int q = 0; q < NQ; q++) {
                     int a = 0;
-                    a = dp4<DT>(qv[q].x, cur.x, a); a = dp4<DT>(qv[q].y, cur.y, a);
-                    a = dp4<DT>(qv[q].z, cur.z, a); a = dp4<DT>(qv[q].w, cur.w, a);
+                    a = dp4<DT>(qv[q].x, cv.x, a); a = dp4<DT>(qv[q].y, cv.y, a);
+                    a = dp4<DT>(qv[q].z, cv.z, a); a = dp4<DT>(qv[q].w, cv.w, a);
                     iacc[q][r] = OP == OP_L2 ? xx - 2 * a : a; facc[q][r] = 0.0f;
                 }
             }
@@ -422,6 +437,12 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
         g = more ? gn : groups;
 #pragma unroll
         for (int c = 0; c < CNT; c++) xn[c] = xn_n[c];
+    };
+    uint4 y[R];
+    while (g < groups) {
+        step(x, y);
+        if (g >= groups) break;
+        step(y, x);
     }
 }
 
