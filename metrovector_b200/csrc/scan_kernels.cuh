@@ -145,13 +145,30 @@ __device__ __forceinline__ int reduce_rows(T (&v)[R], int lane) {
 template <int R, int LPR> struct RowsLeft { static constexpr int CNT = (R / LPR) > 1 ? (R / LPR) : 1; static constexpr int DUP = LPR > R ? LPR / R : 1; };
 
 // offer the candidates held by the lanes of a warp (kInf = nothing) to the warp's running list
-__device__ __forceinline__ void offer(u64 pk, u64* list, int k, u64& thr, int& pos, int lane) {
+// k <= 32: the warp's running list lives in registers, one entry per lane (lanes >= k hold 0 and never
+// are the maximum); an insert overwrites the lane holding the current maximum and re-reduces (max, lane).
+__device__ __forceinline__ void reg_list_insert(u64& mine, int k, u64 cand, u64& thr, int& pos, int lane) {
+    if (lane == pos) mine = cand;
+    u64 m = lane < k ? mine : 0ull;
+    int mp = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const u64 om = shfl_xor_u64(m, off);
+        const int op = __shfl_xor_sync(0xffffffffu, mp, off);
+        if (om > m || (om == m && op < mp)) { m = om; mp = op; }
+    }
+    thr = m; pos = mp;
+}
+__device__ __forceinline__ void offer(u64 pk, u64* list, int k, u64& thr, int& pos, int lane, u64& mine, bool regmode) {
     unsigned hits = __ballot_sync(0xffffffffu, pk < thr);
     while (hits) {
         const int src = __ffs(hits) - 1;
         hits &= hits - 1;
         const u64 c = shfl_u64(pk, src);
-        if (c < thr) list_insert(list, k, c, thr, pos, lane);
+        if (c < thr) {
+            if (regmode) reg_list_insert(mine, k, c, thr, pos, lane);
+            else list_insert(list, k, c, thr, pos, lane);
+        }
     }
 }
 
@@ -177,8 +194,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
     stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
 
     u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
+    u64 regl[NQ];                            // register-resident list entry of this lane (k <= 32)
+    const bool regmode = p.k <= 32;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) { thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; }
+    for (int q = 0; q < NQ; q++) { thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; regl[q] = lane < (int)p.k ? kInf : 0ull; }
 
     const uint32_t n = (uint32_t)p.n;
     const uint32_t pitch = p.pitch;
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
                 if (!F && OP == OP_L2) pk = ((u64)ordered_i32(qc[q].qq + iv) << 32) | row;
                 else pk = finalize<DT>(p.metric, fv, iv, 0, qc[q], xn, row);
             }
-            offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane);
+            offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane, regl[q], regmode);
         }
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -310,6 +329,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
     }
     };
     if (ragged) run(std::true_type{}); else run(std::false_type{});
+    if (regmode) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) if (lane < (int)p.k) lists[(size_t)q * p.P + warp * p.k + lane] = regl[q];
+    }
     emit_cta_lists<NQ>(p, lists);
 }
 
@@ -328,10 +351,12 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
     const int li = lane & (LPR - 1), ri = lane / LPR;
 
     u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
+    u64 regl[NQ];                            // register-resident list entry of this lane (k <= 32)
+    const bool regmode = p.k <= 32;
     float qf[NQ][F ? EPC : 1]; uint4 qv[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-        thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q];
+        thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; regl[q] = lane < (int)p.k ? kInf : 0ull;
         if (F) {
             const float* qb = reinterpret_cast<const float*>(q_s) + (size_t)q * dpad;
             float4 a = reinterpret_cast<const float4*>(qb)[li];
@@ -431,7 +456,7 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
                     if (!F && OP == OP_L2) pk = ((u64)ordered_i32(qc[q].qq + iacc[q][c]) << 32) | row;
                     else pk = finalize<DT>(p.metric, facc[q][c], iacc[q][c], 0, qc[q], xn[c], row);
                 }
-                offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane);
+                offer(pk, lists + (size_t)q * p.P + warp * p.k, (int)p.k, thr[q], pos[q], lane, regl[q], regmode);
             }
         }
         g = more ? gn : groups;
@@ -443,6 +468,10 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
         step(x, y);
         if (g >= groups) break;
         step(y, x);
+    }
+    if (regmode) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) if (lane < (int)p.k) lists[(size_t)q * p.P + warp * p.k + lane] = regl[q];
     }
 }
 

@@ -1,0 +1,6 @@
+#!/bin/bash
+A="python bench.py --workload A --steps 5 --warmup 3 --no-cpu"
+$A > gpurun_out/plain_A.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:scan_topk -s 4 -c 1 -o /tmp/prof_A $A > gpurun_out/ncu_A.log 2>&1
+ncu -i /tmp/prof_A.ncu-rep --page raw --csv > gpurun_out/prof_A_raw.csv 2>/dev/null
+ncu -i /tmp/prof_A.ncu-rep --page source --csv > gpurun_out/prof_A_source.csv 2>/dev/null
+ncu -i /tmp/prof_A.ncu-rep --page details > gpurun_out/prof_A_details.txt 2>/dev/null
