@@ -180,6 +180,15 @@ def main():
 
     import torch
     import torch.distributed as dist
+    lib = os.path.join(ROOT, "metrovector_b200", "libmvf_b200.so")
+    if not os.path.exists(lib) and local_rank == 0:      # fresh checkout on the box: build in-tree (nvcc, sm_100a)
+        import subprocess
+        subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "metrovector_b200", "csrc")], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for _ in range(600):                                    # other ranks wait for rank 0's build
+        if os.path.exists(lib):
+            break
+        time.sleep(1)
     import metrovector_b200 as mv
 
     n, d, dt, metric, k, batch = WORKLOADS[args.workload]
