@@ -202,10 +202,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem;
     u64* scratch = reinterpret_cast<u64*>(ring + STAGES * STAGE_BYTES);           // [epilogue warps][cap]
-    float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [2][BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 2 * BN);                   // full[S] empty[S] tfull[2] tempty[2]
+    float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [epilogue warps][2][EPI_COLS], warp-private
+    uint64_t* bars = reinterpret_cast<uint64_t*>(prm + (EPI_THREADS / 32) * 2 * EPI_COLS);   // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
-    uint32_t* valid_s = tmem_slot + 4;                                                    // [2][BN / 32] live-column words
+    uint32_t* valid_s = tmem_slot + 4;                                                    // [epilogue warps][2][EPI_COLS / 32] live-column words
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES);
@@ -298,10 +298,14 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
         u64* const cta_cand = p.cand + ((size_t)blockIdx.x * EPI_GROUPS + grp) * BM * p.cap;
         u64* mybuf = cta_cand + (size_t)qrow * p.cap;
-        // this tile's per-column parameter, loaded one tile ahead (1 column per thread), and whether the
-        // column is a live row (inside the database, not deleted / filtered out)
-        auto load_param = [&](uint32_t t, bool* live) -> float {
-            const uint64_t row = (uint64_t)t * BN + etid;
+        // Per-column parameter of the ranking value and whether the column is a live row (inside the database,
+        // not deleted / filtered out).  Every epilogue warp stages the EPI_COLS columns of ITS half in a private
+        // shared-memory slice, one tile ahead (4 columns per lane), so the epilogue needs no CTA-wide barrier.
+        constexpr int CPLANE = EPI_COLS / 32;
+        float* my_prm = prm + (size_t)(warp - 2) * 2 * EPI_COLS;
+        uint32_t* my_valid = valid_s + (warp - 2) * 2 * CPLANE;
+        auto load_param = [&](uint32_t t, int j, bool* live) -> float {
+            const uint64_t row = (uint64_t)t * BN + grp * EPI_COLS + j * 32 + lane;
             bool ok = row < p.n;
             if (ok && p.mask != nullptr) ok = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;
             *live = ok;
@@ -336,21 +340,29 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             };
             refresh_threshold();
             {
-                float* pr = prm + acc * BN;
-                bool live0;
-                pr[etid] = load_param(t0, &live0);
-                const unsigned vw0 = __ballot_sync(0xffffffffu, live0);
-                if (lane == 0) valid_s[acc * (BN / 32) + (warp - 2)] = vw0;
+                float* pr = my_prm + acc * EPI_COLS;
+#pragma unroll
+                for (int j = 0; j < CPLANE; j++) {
+                    bool live0;
+                    pr[j * 32 + lane] = load_param(t0, j, &live0);
+                    const unsigned vw0 = __ballot_sync(0xffffffffu, live0);
+                    if (lane == 0) my_valid[acc * CPLANE + j] = vw0;
+                }
                 const uint32_t g0 = __ldcg(p.gthr + q);
                 if (g0 < thr_key) { thr_key = g0; refresh_threshold(); }
-                epi_bar_sync();
+                __syncwarp();
             }
             for (uint32_t t = t0; t < t1; t++) {
-                const float* pr = prm + acc * BN;
-                float nx0 = 0.f;
-                unsigned nvw = 0;
-                if (t + 1 < t1) { bool lv; nx0 = load_param(t + 1, &lv); nvw = __ballot_sync(0xffffffffu, lv); }
-                const uint32_t* vs = valid_s + acc * (BN / 32) + grp * (EPI_COLS / 32);
+                const float* pr = my_prm + acc * EPI_COLS;
+                float nx[CPLANE];
+                unsigned nvw[CPLANE];
+#pragma unroll
+                for (int j = 0; j < CPLANE; j++) { nx[j] = 0.f; nvw[j] = 0; }
+                if (t + 1 < t1) {
+#pragma unroll
+                    for (int j = 0; j < CPLANE; j++) { bool lv; nx[j] = load_param(t + 1, j, &lv); nvw[j] = __ballot_sync(0xffffffffu, lv); }
+                }
+                const uint32_t* vs = my_valid + acc * CPLANE;
                 // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen.
                 // The word is read from L2 now and applied after this tile, so its latency is hidden.
                 const uint32_t gk = __ldcg(p.gthr + q);
@@ -368,7 +380,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     uint32_t (&v)[32] = vv[hh];
                     const int cc = c2 * LDG + hh;
                     const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
-                    const float4* pr4 = reinterpret_cast<const float4*>(pr + grp * EPI_COLS + cc * 32);
+                    const float4* pr4 = reinterpret_cast<const float4*>(pr + cc * 32);
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; j4++) {
@@ -434,12 +446,15 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // all epilogue warps -> accumulator free
                 if (gk < thr_key) { thr_key = gk; refresh_threshold(); }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (t + 1 < t1) {                                          // publish the next tile's parameters
-                    float* prn = prm + acc * BN;
-                    prn[etid] = nx0;
-                    if (lane == 0) valid_s[acc * (BN / 32) + (warp - 2)] = nvw;
+                if (t + 1 < t1) {                                          // publish the next tile's parameters (warp-private)
+                    float* prn = my_prm + acc * EPI_COLS;
+#pragma unroll
+                    for (int j = 0; j < CPLANE; j++) {
+                        prn[j * 32 + lane] = nx[j];
+                        if (lane == 0) my_valid[acc * CPLANE + j] = nvw[j];
+                    }
                 }
-                epi_bar_sync();
+                __syncwarp();
             }
             // end of the work item: every query's buffer becomes a sorted list of its k best
             for (int owner = 0; owner < 32; owner++) {

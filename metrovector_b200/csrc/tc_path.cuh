@@ -76,8 +76,8 @@ inline void init(TcState& st) {
 
 inline int stages_for_cap(uint32_t cap) { return cap > 256 ? 3 : 4; }   // the sort scratch of k > 64 costs one operand stage
 inline size_t smem_bytes(uint32_t cap) {
-    return 1024 + (size_t)stages_for_cap(cap) * STAGE_BYTES + (EPI_THREADS / 32) * (size_t)cap * 8 + 2 * BN * 4 +
-           (2 * MAX_STAGES + 4) * 8 + 16 + 2 * (BN / 32) * 4 + 16;
+    return 1024 + (size_t)stages_for_cap(cap) * STAGE_BYTES + (EPI_THREADS / 32) * (size_t)cap * 8 +
+           (EPI_THREADS / 32) * 2 * EPI_COLS * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + (EPI_THREADS / 32) * 2 * (EPI_COLS / 32) * 4 + 16;
 }
 inline uint32_t cap_for_k(uint32_t k) {
     static const int big = std::getenv("MVF_TC_BIGCAP") ? std::atoi(std::getenv("MVF_TC_BIGCAP")) : 0;

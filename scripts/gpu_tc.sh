@@ -1,9 +1,6 @@
 #!/bin/bash
 # tensor-core path: tests under a timeout (a barrier bug must not hold the box), then the batched benches
-timeout 300 python -m pytest tests/test_gpu_tc.py -x -q 2>&1 | tail -15
-for CLV in 2 1; do
-echo "== MVF_TC_CLUSTER=$CLV"
-MVF_TC_CLUSTER=$CLV timeout 600 python scripts/bench_summary.py C --steps 8 --warmup 3
-MVF_TC_CLUSTER=$CLV timeout 600 python scripts/bench_summary.py D1024 --steps 8 --warmup 3 --rows 20000000
-MVF_TC_CLUSTER=$CLV timeout 600 python scripts/bench_summary.py E1024 --steps 8 --warmup 3 --rows 100000000
-done
+timeout 300 python -m pytest tests/test_gpu_tc.py -x -q 2>&1 | tail -5
+timeout 600 python scripts/bench_summary.py C --steps 8 --warmup 3
+timeout 600 python scripts/bench_summary.py D1024 --steps 8 --warmup 3 --rows 20000000
+timeout 600 python scripts/bench_summary.py E1024 --steps 8 --warmup 3 --rows 100000000
