@@ -13,8 +13,9 @@
 // query's current k-th best (threshold in a register, rare appends to a per-query buffer, warp-
 // cooperative bitonic compaction when a buffer fills).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = two epilogue warpgroups (TMEM lane quarter = warp_id % 4, column half = group).
+// Warp roles (64 + 128*EG threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then EG
+// epilogue warpgroups (TMEM lane quarter = warp_id % 4, column slice = group), each warp decoupled from the
+// others (no CTA-wide barrier in the steady state).
 // Replaces the same reference loop as K1 (examples/similarity_search.rs:147-169) for large batches.
 #pragma once
 #include <cuda.h>
@@ -37,18 +38,17 @@ constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * BKB;  // 16 KiB
 constexpr int B_BYTES = BN * BKB;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_GROUPS = 2;      // epilogue warpgroups: each takes BN / EPI_GROUPS columns of every tile
-constexpr int EPI_THREADS = 128 * EPI_GROUPS;
-constexpr int THREADS = 64 + EPI_THREADS;
-constexpr int EPI_COLS = BN / EPI_GROUPS;
+// epilogue warpgroups (template parameter EG = 2 or 4): each takes BN / EG columns of every tile.  Short rows
+// (K of one or two 128-byte blocks) leave only 512-1024 MMA cycles per tile, so they get 4 groups.
+constexpr int threads_for(int eg) { return 64 + 128 * eg; }
 constexpr int MAX_CAP = 512;       // candidate buffer entries per query (power of two)
 
 struct TcParams {
     const float* norm;             // sqrt(sum x^2) per resident row
     const float* sq;               // sum x^2 per row (f32, or int32 bits for integer spaces)
     const uint32_t* mask;          // optional row mask (bit set = excluded), same layout as ScanParams::mask
-    u64* cand;                     // [gridDim.x][EPI_GROUPS][BM][cap] scratch candidate buffers
-    u64* out_lists;                // [nq][chunks*EPI_GROUPS][k] sorted lists (key = ordered ranking value, id = local row)
+    u64* cand;                     // [gridDim.x][EG][BM][cap] scratch candidate buffers
+    u64* out_lists;                // [nq][chunks*EG][k] sorted lists (key = ordered ranking value, id = local row)
     float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
     uint32_t* gthr;                // [(mtiles rounded up to the cluster size)*BM] tightest k-th-best key any CTA has seen per query (atomicMin)
     uint64_t n;                    // resident rows
@@ -146,7 +146,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 128 bytes, 8-row groups
 // 1024 bytes apart): start>>4 | LBO=1 | SBO=64 | version=1 | layout SWIZZLE_128B
@@ -194,9 +193,10 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // tiles; each CTA fetches half of the 256-row database tile and TMA-multicasts it into both CTAs'
 // shared memory, so L2 -> SM operand traffic per tile drops from 576 KB to 384 KB and the pair
 // stays in lockstep on the same rows.
-template <bool INT, int MODE, int STAGES, int CL, int LDG>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool INT, int MODE, int STAGES, int CL, int EG>
+__global__ void __launch_bounds__(threads_for(EG), 1)
 gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+    constexpr int EPI_GROUPS = EG, EPI_THREADS = 128 * EG, EPI_COLS = BN / EG, LDG = 1;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve shared memory: operand ring (1024-byte aligned) | sort scratch | column params | barriers
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -294,7 +294,6 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31
         const int grp = (warp - 2) >> 2;                                // column half
         const int qrow = quarter * 32 + lane;                           // query row inside the tile
-        const int etid = (warp - 2) * 32 + lane;                        // 0..255 = the column this thread stages
         u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
         u64* const cta_cand = p.cand + ((size_t)blockIdx.x * EPI_GROUPS + grp) * BM * p.cap;
         u64* mybuf = cta_cand + (size_t)qrow * p.cap;

@@ -42,7 +42,7 @@ struct TcState {
     EncodeTiledFn encode = nullptr;
     Buf qprep, qconst, cand, lists, dump, gthr;
     int l2_prefetch = 0;           // (measured slower: the kernel is power-capped, extra L2 traffic costs clocks) database tiles prefetched into L2 ahead of the TMA loads (MVF_TC_PREFETCH=0..4)
-    int ld_group = 1;              // TMEM loads issued per tcgen05.wait::ld in the epilogue (MVF_TC_LDG=1|2)
+    int epi_groups = 0;            // 0 = by row length (4 epilogue warpgroups for K <= 256 bytes, else 2); MVF_TC_EPI_GROUPS=2|4
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
     // auto path: batches at least this large go to the tensor cores.  Measured crossover (scripts/crossover.py):
     // f16 768-d rows: the scan kernel pays a convert + FMA per element per query and loses from 4 queries on;
@@ -70,14 +70,18 @@ inline void init(TcState& st) {
     st.encode = (EncodeTiledFn)fn;
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch_f16 = st.min_batch_i8 = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
-    if (const char* c = std::getenv("MVF_TC_LDG")) st.ld_group = std::atoi(c) == 2 ? 2 : 1;
+    if (const char* c = std::getenv("MVF_TC_EPI_GROUPS")) st.epi_groups = std::atoi(c) == 4 ? 4 : (std::atoi(c) == 2 ? 2 : 0);
     if (const char* c = std::getenv("MVF_TC_PREFETCH")) st.l2_prefetch = std::max(0, std::min(4, std::atoi(c)));
 }
 
-inline int stages_for_cap(uint32_t cap) { return cap > 256 ? 3 : 4; }   // the sort scratch of k > 64 costs one operand stage
-inline size_t smem_bytes(uint32_t cap) {
-    return 1024 + (size_t)stages_for_cap(cap) * STAGE_BYTES + (EPI_THREADS / 32) * (size_t)cap * 8 +
-           (EPI_THREADS / 32) * 2 * EPI_COLS * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + (EPI_THREADS / 32) * 2 * (EPI_COLS / 32) * 4 + 16;
+// shared memory: operand ring + per-warp sort scratch + per-warp column parameters + barriers
+inline size_t smem_bytes(uint32_t cap, int eg, int stages) {
+    const size_t warps = 4 * (size_t)eg, cols = BN / eg;
+    return 1024 + (size_t)stages * STAGE_BYTES + warps * (size_t)cap * 8 + warps * 2 * cols * 4 + (2 * MAX_STAGES + 4) * 8 + 16 +
+           warps * 2 * (cols / 32) * 4 + 16;
+}
+inline int stages_for(uint32_t cap, int eg) {   // the sort scratch of large k / many epilogue warps costs one operand stage
+    return smem_bytes(cap, eg, 4) <= 227 * 1024 ? 4 : 3;
 }
 inline uint32_t cap_for_k(uint32_t k) {
     static const int big = std::getenv("MVF_TC_BIGCAP") ? std::atoi(std::getenv("MVF_TC_BIGCAP")) : 0;
@@ -99,18 +103,18 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
     return nq >= (uint32_t)(f16 ? st.min_batch_f16 : st.min_batch_i8) && n >= 4096;
 }
 
-template <bool INT, int MODE, int LDG>
+template <bool INT, int MODE, int EG>
 inline const void* select_kernel_sc(int stages, int cl) {
-    if (stages == 3) return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 3, 2, LDG> : (const void*)gemm_topk_tc<INT, MODE, 3, 1, LDG>;
-    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 4, 2, LDG> : (const void*)gemm_topk_tc<INT, MODE, 4, 1, LDG>;
+    if (stages == 3) return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 3, 2, EG> : (const void*)gemm_topk_tc<INT, MODE, 3, 1, EG>;
+    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 4, 2, EG> : (const void*)gemm_topk_tc<INT, MODE, 4, 1, EG>;
 }
-template <int LDG>
+template <int EG>
 inline const void* select_kernel_l(bool is_int, bool l2, int stages, int cl) {
-    if (is_int) return l2 ? select_kernel_sc<true, 0, LDG>(stages, cl) : select_kernel_sc<true, 1, LDG>(stages, cl);
-    return l2 ? select_kernel_sc<false, 0, LDG>(stages, cl) : select_kernel_sc<false, 1, LDG>(stages, cl);
+    if (is_int) return l2 ? select_kernel_sc<true, 0, EG>(stages, cl) : select_kernel_sc<true, 1, EG>(stages, cl);
+    return l2 ? select_kernel_sc<false, 0, EG>(stages, cl) : select_kernel_sc<false, 1, EG>(stages, cl);
 }
-inline const void* select_kernel(bool is_int, bool l2, int stages, int cl, int ldg) {
-    return ldg == 2 ? select_kernel_l<2>(is_int, l2, stages, cl) : select_kernel_l<1>(is_int, l2, stages, cl);
+inline const void* select_kernel(bool is_int, bool l2, int stages, int cl, int eg) {
+    return eg == 4 ? select_kernel_l<4>(is_int, l2, stages, cl) : select_kernel_l<2>(is_int, l2, stages, cl);
 }
 
 inline void make_map(TcState& st, CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint32_t d, uint64_t pitch,
@@ -144,11 +148,15 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     const uint32_t items = mgroups * chunks;
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count / CL, items) * CL;
     const uint32_t cap = cap_for_k(a.k);
+    const uint32_t kblocks = (a.d * es + BKB - 1) / BKB;
+    int EG = st.epi_groups ? st.epi_groups : (kblocks <= 2 ? 4 : 2);
+    if (smem_bytes(cap, EG, 3) > 227 * 1024) EG = 2;
+    const int stages = stages_for(cap, EG);
 
     st.qprep.reserve((size_t)mtiles * BM * qpitch);
     st.qconst.reserve((size_t)a.nq * 4);
-    st.cand.reserve((size_t)grid * EPI_GROUPS * BM * cap * 8);
-    st.lists.reserve((size_t)a.nq * chunks * EPI_GROUPS * a.k * 8);
+    st.cand.reserve((size_t)grid * EG * BM * cap * 8);
+    st.lists.reserve((size_t)a.nq * chunks * EG * a.k * 8);
     st.gthr.reserve((size_t)mgroups * CL * BM * 4);
     TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mgroups * CL * BM * 4, stream));
     uint64_t launches = 0;
@@ -172,7 +180,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
-    p.kblocks = (a.d * es + BKB - 1) / BKB;
+    p.kblocks = kblocks;
     p.mtiles = mtiles; p.ntiles = ntiles; p.chunks = chunks; p.tiles_per_chunk = tiles_per_chunk;
     p.metric = a.metric; p.is_int = is_int ? 1 : 0;
     const uint32_t fmt = a.dtype == k::DT_I8 ? 1u : 0u;     // kind::i8: 0 = unsigned, 1 = signed; kind::f16: 0 = F16
@@ -184,12 +192,12 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
         p.dump = (float*)st.dump.p;
     }
     const bool l2 = a.metric == k::M_L2;
-    const void* fn = select_kernel(is_int, l2, cap > 256 ? 3 : 4, (int)CL, st.ld_group);
-    const size_t smem = smem_bytes(cap);
+    const void* fn = select_kernel(is_int, l2, stages, (int)CL, EG);
+    const size_t smem = smem_bytes(cap, EG, stages);
     TC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&map_q, (void*)&map_x, (void*)&p};
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads_for(EG)); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -198,7 +206,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     TC_CUDA_CHECK(cudaGetLastError());
     launches++;
     SearchResult r;
-    r.lists = (const u64*)st.lists.p; r.chunks = chunks * EPI_GROUPS; r.qconst = (const float*)st.qconst.p;
+    r.lists = (const u64*)st.lists.p; r.chunks = chunks * EG; r.qconst = (const float*)st.qconst.p;
     r.dump = (const float*)st.dump.p; r.dump_cols = ntiles * BN; r.launches = launches;
     return r;
 }

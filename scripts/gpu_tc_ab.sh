@@ -1,6 +1,6 @@
 #!/bin/bash
 # same-box A/B of a tensor-path knob: alternates the settings so power/thermal state is shared
-VAR=${1:-MVF_TC_LDG}; shift
+VAR=${1:-MVF_TC_EPI_GROUPS}; shift
 timeout 300 python -m pytest tests/test_gpu_tc.py -x -q 2>&1 | tail -3
 for rep in 1 2; do for V in "$@"; do
 echo "== $VAR=$V (rep $rep)"
