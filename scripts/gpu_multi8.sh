@@ -1,3 +1,2 @@
 #!/bin/bash
-WORKLOADS="B D" ./scripts/gpu_multi.sh 8
-STEPS=5 WORKLOADS="D1024" ./scripts/gpu_multi.sh 8 | tail -2
+WORKLOADS="D D1024 E E1024 C B" ./scripts/gpu_multi.sh 8
