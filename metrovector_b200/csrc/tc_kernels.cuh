@@ -380,7 +380,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     const int cc = c2 * LDG + hh;
                     const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
                     const float4* pr4 = reinterpret_cast<const float4*>(pr + cc * 32);
-                    uint32_t mask = 0;
+                    // ranking values in place, and their minimum: almost every 32-column group holds nothing that
+                    // beats the threshold, so the per-element compare + mask is only built when the minimum does
+                    float fmin_ = __int_as_float(0x7f800000);
+                    int imin_ = 0x7fffffff;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; j4++) {
                         const float4 pq = pr4[j4];
@@ -392,13 +395,21 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                                 const int a = (int)v[j];
                                 const int s = MODE == 0 ? __float_as_int(pj[e]) - 2 * a : -a;
                                 v[j] = (uint32_t)s;
-                                if (s <= thr_i) mask |= 1u << j;
+                                imin_ = min(imin_, s);
                             } else {
                                 const float a = __uint_as_float(v[j]);
                                 const float s = MODE == 0 ? fmaf(a, -2.0f, pj[e]) : a * pj[e];
                                 v[j] = __float_as_uint(s);
-                                if (s <= thr_f) mask |= 1u << j;
+                                fmin_ = fminf(fmin_, s);
                             }
+                        }
+                    }
+                    uint32_t mask = 0;
+                    if (INT ? (imin_ <= thr_i) : (fmin_ <= thr_f)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if (INT) { if ((int)v[j] <= thr_i) mask |= 1u << j; }
+                            else { if (__uint_as_float(v[j]) <= thr_f) mask |= 1u << j; }
                         }
                     }
                     mask &= vs[cc];                                      // rows past the end, deleted or filtered out
