@@ -217,6 +217,14 @@ void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, ui
 }
 
 void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
+    // many queries: one warp per query straight from L2 (latency hidden by the other warps)
+    if (nq >= 64 && mp.nlists > 0 && mp.nlists <= 32u * k::kMergeMaxHeads) {
+        mp.seg_lists = mp.nlists; mp.P = 0;
+        k::merge_topk_warp<<<(nq + 7) / 8, 256, 0, g->stream>>>(mp, nq);
+        CUDA_CHECK(cudaGetLastError());
+        g->all_launches++;
+        return;
+    }
     // fast flavour: the lists of one CTA staged in shared memory, two-level warp tournament; when
     // they do not fit, a segmented pass first reduces them to a few intermediate lists
     const size_t budget = std::min<size_t>(g->smem_optin, 200 * 1024);

@@ -286,6 +286,51 @@ __global__ void __launch_bounds__(1024) merge_topk_tournament(const MergeParams 
     }
 }
 
+
+// K3, batch flavour: one WARP per query, list heads read straight from global memory (L2) with the next
+// element of every list prefetched one step ahead.  With thousands of queries every SM holds dozens of
+// independent merges, so the per-output latency is hidden by other warps instead of by shared-memory
+// staging (the CTA-per-query tournament above is the low-latency choice for a handful of queries).
+__global__ void __launch_bounds__(256) merge_topk_warp(const MergeParams p, uint32_t nq) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const u64* src = p.in + (size_t)q * p.q_stride;
+    uint32_t idx[kMergeMaxHeads];
+    u64 head[kMergeMaxHeads], nxt[kMergeMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMergeMaxHeads; h++) {
+        idx[h] = 0;
+        const uint32_t li = (uint32_t)h * 32 + lane;
+        head[h] = li < p.nlists ? __ldcg(src + (size_t)li * p.list_stride) : kInf;
+        nxt[h] = (li < p.nlists && p.k > 1) ? __ldcg(src + (size_t)li * p.list_stride + 1) : kInf;
+    }
+    for (uint32_t j = 0; j < p.k; j++) {
+        u64 mine = head[0];
+#pragma unroll
+        for (int h = 1; h < kMergeMaxHeads; h++) mine = head[h] < mine ? head[h] : mine;
+        const u64 m = warp_min_u64(mine);
+        if (lane == 0) emit_result(p, q, j, m);
+        if (m == kInf) {                                   // every list is exhausted: pad the rest
+            for (uint32_t t = j + 1 + lane; t < p.k; t += 32) emit_result(p, q, t, kInf);
+            break;
+        }
+        const unsigned owners = __ballot_sync(0xffffffffu, mine == m);
+        if (lane == (uint32_t)(__ffs(owners) - 1)) {
+            bool adv = false;
+#pragma unroll
+            for (int h = 0; h < kMergeMaxHeads; h++) {
+                if (!adv && head[h] == m) {
+                    adv = true;
+                    const uint32_t li = (uint32_t)h * 32 + lane;
+                    idx[h]++;
+                    head[h] = idx[h] < p.k ? nxt[h] : kInf;
+                    nxt[h] = idx[h] + 1 < p.k ? __ldcg(src + (size_t)li * p.list_stride + idx[h] + 1) : kInf;
+                }
+            }
+        }
+    }
+}
 #endif  // MVF_ENGINE_TU
 
 // ------------------------------------------------------------------------------------------------
