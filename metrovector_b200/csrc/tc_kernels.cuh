@@ -59,7 +59,6 @@ struct TcParams {
     int is_int;                    // 0: f16 operands / f32 accum, 1: int8 operands / s32 accum
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t l2_prefetch_tiles;    // database tiles the producer prefetches into L2 ahead of its TMA loads (0 = off)
-    uint32_t debug_flags;          // bit 0: always build the hit mask (bypass the minimum early-out)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -310,8 +309,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             if (ok && p.mask != nullptr) ok = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;
             *live = ok;
             if (!ok) return __int_as_float(0);
-            if (MODE == 0 && INT) return __int_as_float(__float_as_int(p.sq[row]) + (int)0x80000000);   // |x|^2, biased to the unsigned key order
-            if (MODE == 0) return p.sq[row];                              // |x|^2
+            if (MODE == 0) return p.sq[row];                              // |x|^2 (int32 bits for integer spaces)
             if (INT) return __int_as_float(0);
             if (p.metric == k::M_COS) { const float nm = p.norm[row]; return nm > 0.f ? -1.0f / nm : 0.0f; }
             return -1.0f;
@@ -330,14 +328,20 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             // the strict case compares against the next smaller key.
             uint32_t thr_key = 0xffffffffu, loc_key = 0xffffffffu;
             float thr_f = __int_as_float(0x7f800000);                   // +inf: everything passes until k are known
-            uint32_t thr_i = 0xffffffffu;                                // integer spaces compare order-preserving unsigned keys
+            // Integer spaces.  MODE 0 ranks s = |x|^2 - 2a: hit iff s <= thr_i.  MODE 1 ranks s = -a, but the
+            // epilogue never negates: it looks for the LARGEST a and a hit is a > ~thr_i (== -a <= thr_i for every
+            // thr_i, with no overflow at either end).  Besides saving 32 negations per group this keeps ptxas
+            // (12.9) from folding the negations into the 3-input minimum, which it does incorrectly: only the
+            // outer two operands of each VIMNMX3 came out negated and the early-out skipped real hits.
+            int thr_i = 0x7fffffff;
+            auto set_thr_i = [&](int t) { thr_i = (MODE == 0) ? t : ~t; };
             auto refresh_threshold = [&]() {
-                if (q >= p.nq) { thr_f = __int_as_float(0xff800000); thr_i = 0u; return; }   // padding row of the query tile: nothing passes
-                if (thr_key == 0xffffffffu) { thr_f = __int_as_float(0x7f800000); thr_i = 0xffffffffu; return; }
+                if (q >= p.nq) { thr_f = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }   // padding row of the query tile: nothing passes
+                if (thr_key == 0xffffffffu) { thr_f = __int_as_float(0x7f800000); set_thr_i(0x7fffffff); return; }
                 const bool ties = thr_key < loc_key;
-                if (!ties && thr_key == 0) { thr_f = __int_as_float(0xff800000); thr_i = 0u; return; }
+                if (!ties && thr_key == 0) { thr_f = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }
                 const uint32_t ck = ties ? thr_key : thr_key - 1;
-                if (INT) thr_i = ck; else thr_f = k::unordered_f32(ck);
+                if (INT) set_thr_i((int)(ck ^ 0x80000000u)); else thr_f = k::unordered_f32(ck);
             };
             refresh_threshold();
             {
@@ -385,7 +389,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     // ranking values in place, and their minimum: almost every 32-column group holds nothing that
                     // beats the threshold, so the per-element compare + mask is only built when the minimum does
                     float fmin_ = __int_as_float(0x7f800000);
-                    uint32_t umin_ = 0xffffffffu;
+                    int iext_ = MODE == 0 ? 0x7fffffff : (int)0x80000000;     // min of s (MODE 0) / max of a (MODE 1)
 #pragma unroll
                     for (int j4 = 0; j4 < 8; j4++) {
                         const float4 pq = pr4[j4];
@@ -394,12 +398,14 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         for (int e = 0; e < 4; e++) {
                             const int j = j4 * 4 + e;
                             if (INT) {
-                                // order-preserving unsigned key of s = |x|^2 - 2a (or -a): s + 2^31; the bias rides in
-                                // the column parameter (MODE 0) or the constant (MODE 1), so it costs nothing
-                                const uint32_t a = v[j];
-                                const uint32_t u = MODE == 0 ? (uint32_t)__float_as_int(pj[e]) - 2u * a : 0x80000000u - a;
-                                v[j] = u;
-                                umin_ = min(umin_, u);
+                                const int a = (int)v[j];
+                                if (MODE == 0) {
+                                    const int s = __float_as_int(pj[e]) - 2 * a;
+                                    v[j] = (uint32_t)s;
+                                    iext_ = min(iext_, s);
+                                } else {
+                                    iext_ = max(iext_, a);
+                                }
                             } else {
                                 const float a = __uint_as_float(v[j]);
                                 const float s = MODE == 0 ? fmaf(a, -2.0f, pj[e]) : a * pj[e];
@@ -409,10 +415,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         }
                     }
                     uint32_t mask = 0;
-                    if ((p.debug_flags & 1u) || (INT ? (umin_ <= thr_i) : (fmin_ <= thr_f))) {
+                    if (INT ? (MODE == 0 ? iext_ <= thr_i : iext_ > thr_i) : (fmin_ <= thr_f)) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            if (INT) { if (v[j] <= thr_i) mask |= 1u << j; }
+                            if (INT) { if (MODE == 0 ? (int)v[j] <= thr_i : (int)v[j] > thr_i) mask |= 1u << j; }
                             else { if (__uint_as_float(v[j]) <= thr_f) mask |= 1u << j; }
                         }
                     }
@@ -421,13 +427,14 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; j++)
                             p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] =
-                                INT ? (float)(int)(v[j] ^ 0x80000000u) : __uint_as_float(v[j]);
+                                INT ? (float)(MODE == 0 ? (int)v[j] : -(int)v[j]) : __uint_as_float(v[j]);
                     }
                     if (mask) {                                          // rare per thread
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             if (mask & (1u << j)) {
-                                const uint32_t key = INT ? v[j] : k::ordered_f32(__uint_as_float(v[j]));
+                                const uint32_t key = INT ? k::ordered_i32(MODE == 0 ? (int)v[j] : -(int)v[j])
+                                                         : k::ordered_f32(__uint_as_float(v[j]));
                                 mybuf[cnt++] = ((u64)key << 32) | (id0 + j);
                             }
                         }

@@ -186,7 +186,6 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     const uint32_t fmt = a.dtype == k::DT_I8 ? 1u : 0u;     // kind::i8: 0 = unsigned, 1 = signed; kind::f16: 0 = F16
     const uint32_t cfmt = is_int ? 2u : 1u;                  // accumulator: S32 / F32
     p.l2_prefetch_tiles = (uint32_t)st.l2_prefetch;
-    p.debug_flags = std::getenv("MVF_TC_DEBUG") ? (uint32_t)std::atoi(std::getenv("MVF_TC_DEBUG")) : 0u;
     p.idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     if (a.dump) {
         st.dump.reserve((size_t)mtiles * BM * (size_t)ntiles * BN * 4);
