@@ -275,6 +275,21 @@ def main():
             step_device(args.warmup + i)
         prof = eng.profile_read()
         eng.profile(False)
+        # ---- tensor path only: the last batch's first rows again through the bandwidth scan (K1) ----
+        cross = None
+        if prof["last_path"] == 2:
+            nchk = min(batch, 4)
+            ids2 = torch.empty((nchk, k), dtype=torch.int64, device="cuda")
+            sc2 = torch.empty((nchk, k), dtype=torch.float32, device="cuda")
+            eng.set_path(1)
+            jl = (args.warmup + args.steps - 1) % distinct
+            gs.search_device(q_dev.data_ptr() + jl * qbytes, qdt, nchk, k, metric, ids2.data_ptr(), sc2.data_ptr())
+            eng.set_path(args.path)
+            torch.cuda.synchronize()
+            if dt >= 2:
+                cross = bool(torch.equal(ids2, ids_dev[:nchk]))
+            else:
+                cross = bool(torch.allclose(sc2, sc_dev[:nchk], rtol=1e-4, atol=1e-5))
     sampler.stop_flag = True
     sampler.join()
 
@@ -297,7 +312,7 @@ def main():
                 row = mv.synth_fill_host(dt, DB_SEED, int(gid), 1, d)[0]
                 ref, iref, _ = oracle.score_row(row, dt, metric, q0.astype(np.float32) if dt in (0, 1) else q0)
                 ok = ok and (abs(ref - s) <= 1e-3 * max(1.0, abs(ref)))
-            verified = bool(ok and np.all(np.diff(sc[:k] if metric != 1 else -sc[:k]) >= 0))
+            verified = bool(ok and np.all(np.diff(sc[:k] if metric != 1 else -sc[:k]) >= 0) and cross is not False)
         except Exception as ex:   # the oracle is optional equipment for the bench
             verified = "unchecked: %s" % ex
 
@@ -339,6 +354,7 @@ def main():
             "roofline": roof,
             "clocks": sampler.summary(),
             "verified_against_oracle": verified,
+            "tensor_path_cross_checked_vs_scan": cross,
         }
         if world == 1 and not args.no_cpu:
             try:

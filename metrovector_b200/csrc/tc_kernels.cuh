@@ -34,10 +34,11 @@ using k::kInf;
 constexpr int BM = 128;            // queries per tile (TMEM lanes)
 constexpr int BN = 256;            // database rows per tile (TMEM columns, MMA N)
 constexpr int BKB = 128;           // K block in bytes (one 128-byte swizzle row)
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int A_BYTES = BM * BKB;  // 16 KiB
 constexpr int B_BYTES = BN * BKB;  // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;           // one CTA holds the whole database tile
+constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES / 2;  // CTA pair (cta_group::2): each CTA holds half of it
 // epilogue warpgroups (template parameter EG = 2 or 4): each takes BN / EG columns of every tile.  Short rows
 // (K of one or two 128-byte blocks) leave only 512-1024 MMA cycles per tile, so they get 4 groups.
 constexpr int threads_for(int eg) { return 64 + 128 * eg; }
@@ -59,6 +60,9 @@ struct TcParams {
     int is_int;                    // 0: f16 operands / f32 accum, 1: int8 operands / s32 accum
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t l2_prefetch_tiles;    // database tiles the producer prefetches into L2 ahead of its TMA loads (0 = off)
+    uint32_t stages;               // depth of the operand ring (<= MAX_STAGES)
+    uint32_t* progress;            // [items] database tiles each work item's producer has issued (pacing, see sync_window)
+    uint32_t sync_window;          // 0 = off; else a producer stays within this many tiles of the slowest peer on its rows
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -131,6 +135,63 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
             ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a cluster, M = 256 (128 query rows per CTA),
+// each CTA supplies half of the B operand from its own shared memory ----
+template <bool INT>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (INT) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// arrives on the barrier at the same shared-memory offset in every CTA of `mask` once the pair's MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {     // issued by the same warp of both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on the barrier at the same offset in the pair's
+// leader (even) CTA: shared-window addresses of a pair differ in bit 24 only
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals may come from the peer CTA
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -193,15 +254,23 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // tiles; each CTA fetches half of the 256-row database tile and TMA-multicasts it into both CTAs'
 // shared memory, so L2 -> SM operand traffic per tile drops from 576 KB to 384 KB and the pair
 // stays in lockstep on the same rows.
-template <bool INT, int MODE, int STAGES, int CL, int EG>
+// PAIR (with CL = 2): the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per K step: 256 queries x 256 rows,
+// each CTA stages its own 128 query rows and HALF of the database tile (32 KiB per stage instead of 48, so the
+// ring is 5-6 deep), the leader CTA issues, both epilogues drain their own TMEM.  Against the multicast form
+// this cuts the bytes written into each SM's shared memory per tile by a third and halves the tensor core's
+// shared-memory reads of the B operand.
+template <bool INT, int MODE, int CL, int EG, bool PAIR>
 __global__ void __launch_bounds__(threads_for(EG), 1)
 gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+    static_assert(!PAIR || CL == 2, "the pair form needs clusters of two");
     constexpr int EPI_GROUPS = EG, EPI_THREADS = 128 * EG, EPI_COLS = BN / EG, LDG = 1;
+    constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;
+    const uint32_t STAGES = p.stages;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve shared memory: operand ring (1024-byte aligned) | sort scratch | column params | barriers
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem;
-    u64* scratch = reinterpret_cast<u64*>(ring + STAGES * STAGE_BYTES);           // [epilogue warps][cap]
+    u64* scratch = reinterpret_cast<u64*>(ring + STAGES * SB);           // [epilogue warps][cap]
     float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [epilogue warps][2][EPI_COLS], warp-private
     uint64_t* bars = reinterpret_cast<uint64_t*>(prm + (EPI_THREADS / 32) * 2 * EPI_COLS);   // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
@@ -214,11 +283,12 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_x);
-        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, EPI_THREADS / 32); }
+        for (uint32_t s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PAIR ? 1 : CL); }
+        // pair form: the leader's MMA thread waits for the epilogue warps of BOTH CTAs before it overwrites an accumulator
+        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, (PAIR ? 2 : 1) * (EPI_THREADS / 32)); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
     tcgen05_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                                     // peers' barriers exist before any remote arrive
@@ -240,12 +310,42 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 const uint32_t mt = (w % mgroups) * CL + crank, ch = w / mgroups;
                 const uint32_t t0 = ch * p.tiles_per_chunk;
                 const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
+                // Pacing.  The mgroups work items of one run of database tiles execute at the same time on different
+                // clusters and should find those tiles in L2; nothing else keeps them together, and once they drift
+                // apart by more than L2 holds, every one of them streams the rows from HBM again (measured on config
+                // C, 16 items per run: 142 GB read for 15 GB of rows).  So a producer does not run more than
+                // sync_window tiles ahead of the slowest item on the same rows in the same scheduling round.  All CTAs
+                // are resident (grid <= SM count) and an item only ever waits for items of its own round, so the wait
+                // cannot cycle; it is bounded anyway and falls back to "just go".
+                const bool pace = p.sync_window != 0 && crank == 0;
+                const uint32_t round_lo = (w / w_step) * w_step;
+                const uint32_t g_lo = max(ch * mgroups, round_lo), g_hi = min(min((ch + 1) * mgroups, round_lo + w_step), items);
                 for (uint32_t t = t0; t < t1; t++) {
+                    if (pace && ((t - t0) & 3u) == 0) {
+                        const uint32_t r = t - t0;
+                        st_relaxed_gpu(p.progress + w, r);
+                        if (r > p.sync_window) {
+                            for (int spin = 0; spin < 2048; spin++) {
+                                uint32_t slowest = 0xffffffffu;
+                                for (uint32_t x = g_lo; x < g_hi; x++) slowest = min(slowest, ld_relaxed_gpu(p.progress + x));
+                                if (r <= slowest + p.sync_window) break;
+                                __nanosleep(512);
+                            }
+                        }
+                    }
                     for (uint32_t kb = 0; kb < p.kblocks; kb++) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);          // every CTA of the cluster released the slot
-                        const uint32_t a_dst = smem_u32(ring + stage * STAGE_BYTES);
-                        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+                        const uint32_t a_dst = smem_u32(ring + stage * SB);
                         const int kc = (int)(kb * (INT ? 128u : 64u));   // element coordinate along K
+                        if (PAIR) {
+                            // both CTAs' bytes are counted on the leader's barrier, which alone expects them
+                            if (crank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * SB);
+                            tma_load_2d_pair(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
+                            tma_load_2d_pair(a_dst + A_BYTES, &map_x, full0 + 8 * stage, kc, (int)(t * BN + crank * (BN / 2)));
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
+                        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
                         tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
                         if (p.l2_prefetch_tiles && t + p.l2_prefetch_tiles < t1)   // pull a later tile's rows from HBM into L2 now
                             tma_prefetch_l2_2d(&map_x, kc, (int)((t + p.l2_prefetch_tiles) * BN + crank * (BN / CL)));
@@ -257,33 +357,39 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
+                if (pace) st_relaxed_gpu(p.progress + w, 0xffffffffu);     // finished: never holds anyone back
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (lane == 0 && (!PAIR || crank == 0)) {                       // pair form: the leader CTA issues for both
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t w = w_first; w < items; w += w_step) {
                 const uint32_t ch = w / mgroups;
                 const uint32_t t0 = ch * p.tiles_per_chunk;
                 const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
                 for (uint32_t t = t0; t < t1; t++) {
-                    mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+                    if (PAIR) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
+                    else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     for (uint32_t kb = 0; kb < p.kblocks; kb++) {
                         mbar_wait(full0 + 8 * stage, phase);           // TMA bytes have landed
                         tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(ring + stage * STAGE_BYTES);
+                        const uint32_t a_addr = smem_u32(ring + stage * SB);
                         const uint64_t adesc = make_sdesc(a_addr), bdesc = make_sdesc(a_addr + A_BYTES);
 #pragma unroll
-                        for (uint32_t ks = 0; ks < 4; ks++)              // 4 x 32 bytes of K per 128-byte block
-                            umma<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
-                        if (CL > 1) umma_commit_mc(empty0 + 8 * stage, (uint16_t)((1u << CL) - 1));   // slot free in every CTA
+                        for (uint32_t ks = 0; ks < 4; ks++) {            // 4 x 32 bytes of K per 128-byte block
+                            if (PAIR) umma_pair<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                            else umma<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                        }
+                        if (PAIR) umma_commit_pair(empty0 + 8 * stage, 3);
+                        else if (CL > 1) umma_commit_mc(empty0 + 8 * stage, (uint16_t)((1u << CL) - 1));   // slot free in every CTA
                         else umma_commit(empty0 + 8 * stage);            // frees the smem slot when the MMAs retire
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(tfull0 + 8 * acc);                        // accumulator ready for the epilogue
+                    if (PAIR) umma_commit_pair(tfull0 + 8 * acc, 3);      // each CTA's half of the accumulator is ready
+                    else umma_commit(tfull0 + 8 * acc);                   // accumulator ready for the epilogue
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
@@ -464,7 +570,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);           // all epilogue warps -> accumulator free
+                if (lane == 0) {                                         // all epilogue warps -> accumulator free
+                    if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * acc, 0));
+                    else mbar_arrive(tempty0 + 8 * acc);
+                }
                 if (gk < thr_key) { thr_key = gk; refresh_threshold(); }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 if (t + 1 < t1) {                                          // publish the next tile's parameters (warp-private)
@@ -497,7 +606,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     tcgen05_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                                     // no CTA leaves while a peer may still write into it
-    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 1) { tcgen05_fence_after(); if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // query preparation: copy the batch into a 16-byte-pitched operand buffer and compute the

@@ -40,10 +40,12 @@ struct Buf {
 
 struct TcState {
     EncodeTiledFn encode = nullptr;
-    Buf qprep, qconst, cand, lists, dump, gthr;
+    Buf qprep, qconst, cand, lists, dump, gthr, progress;
     int l2_prefetch = 0;           // (measured slower: the kernel is power-capped, extra L2 traffic costs clocks) database tiles prefetched into L2 ahead of the TMA loads (MVF_TC_PREFETCH=0..4)
     int epi_groups = 0;            // 0 = by row length (4 epilogue warpgroups for K <= 256 bytes, else 2); MVF_TC_EPI_GROUPS=2|4
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
+    int sync_window = -1;          // pacing of work items that share database tiles: -1 = auto (on from 8 query-tile groups), 0 = off, else tiles (MVF_TC_SYNC_WINDOW)
+    int pair = 1;                  // clusters of two run cta_group::2 MMAs (256 queries x 256 rows, half the database tile per CTA) instead of multicasting whole tiles (MVF_TC_PAIR=0|1)
     // auto path: batches at least this large go to the tensor cores.  Measured crossover (scripts/crossover.py):
     // f16 768-d rows: the scan kernel pays a convert + FMA per element per query and loses from 4 queries on;
     // uint8 128-d rows: dp4a keeps the scan ahead up to ~7 queries.  MVF_TC_MIN_BATCH overrides both.
@@ -70,18 +72,24 @@ inline void init(TcState& st) {
     st.encode = (EncodeTiledFn)fn;
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch_f16 = st.min_batch_i8 = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
+    if (const char* c = std::getenv("MVF_TC_PAIR")) st.pair = std::max(0, std::min(2, std::atoi(c)));
+    if (const char* c = std::getenv("MVF_TC_SYNC_WINDOW")) st.sync_window = std::max(-1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_EPI_GROUPS")) st.epi_groups = std::atoi(c) == 4 ? 4 : (std::atoi(c) == 2 ? 2 : 0);
     if (const char* c = std::getenv("MVF_TC_PREFETCH")) st.l2_prefetch = std::max(0, std::min(4, std::atoi(c)));
 }
 
 // shared memory: operand ring + per-warp sort scratch + per-warp column parameters + barriers
-inline size_t smem_bytes(uint32_t cap, int eg, int stages) {
+inline size_t smem_bytes(uint32_t cap, int eg, int stages, bool pair) {
     const size_t warps = 4 * (size_t)eg, cols = BN / eg;
-    return 1024 + (size_t)stages * STAGE_BYTES + warps * (size_t)cap * 8 + warps * 2 * cols * 4 + (2 * MAX_STAGES + 4) * 8 + 16 +
-           warps * 2 * (cols / 32) * 4 + 16;
+    return 1024 + (size_t)stages * (pair ? PAIR_STAGE_BYTES : STAGE_BYTES) + warps * (size_t)cap * 8 + warps * 2 * cols * 4 +
+           (2 * MAX_STAGES + 4) * 8 + 16 + warps * 2 * (cols / 32) * 4 + 16;
 }
-inline int stages_for(uint32_t cap, int eg) {   // the sort scratch of large k / many epilogue warps costs one operand stage
-    return smem_bytes(cap, eg, 4) <= 227 * 1024 ? 4 : 3;
+// deepest operand ring that fits beside the sort scratch (large k / many epilogue warps cost stages):
+// 3-4 stages of 48 KiB, or 5-6 of 32 KiB in the pair form
+inline int stages_for(uint32_t cap, int eg, bool pair) {
+    int s = pair ? MAX_STAGES : 4;
+    while (s > 2 && smem_bytes(cap, eg, s, pair) > 227 * 1024) s--;
+    return s;
 }
 inline uint32_t cap_for_k(uint32_t k) {
     static const int big = std::getenv("MVF_TC_BIGCAP") ? std::atoi(std::getenv("MVF_TC_BIGCAP")) : 0;
@@ -104,17 +112,17 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
 }
 
 template <bool INT, int MODE, int EG>
-inline const void* select_kernel_sc(int stages, int cl) {
-    if (stages == 3) return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 3, 2, EG> : (const void*)gemm_topk_tc<INT, MODE, 3, 1, EG>;
-    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 4, 2, EG> : (const void*)gemm_topk_tc<INT, MODE, 4, 1, EG>;
+inline const void* select_kernel_sc(int cl, bool pair) {
+    if (pair) return (const void*)gemm_topk_tc<INT, MODE, 2, EG, true>;
+    return cl == 2 ? (const void*)gemm_topk_tc<INT, MODE, 2, EG, false> : (const void*)gemm_topk_tc<INT, MODE, 1, EG, false>;
 }
 template <int EG>
-inline const void* select_kernel_l(bool is_int, bool l2, int stages, int cl) {
-    if (is_int) return l2 ? select_kernel_sc<true, 0, EG>(stages, cl) : select_kernel_sc<true, 1, EG>(stages, cl);
-    return l2 ? select_kernel_sc<false, 0, EG>(stages, cl) : select_kernel_sc<false, 1, EG>(stages, cl);
+inline const void* select_kernel_l(bool is_int, bool l2, int cl, bool pair) {
+    if (is_int) return l2 ? select_kernel_sc<true, 0, EG>(cl, pair) : select_kernel_sc<true, 1, EG>(cl, pair);
+    return l2 ? select_kernel_sc<false, 0, EG>(cl, pair) : select_kernel_sc<false, 1, EG>(cl, pair);
 }
-inline const void* select_kernel(bool is_int, bool l2, int stages, int cl, int eg) {
-    return eg == 4 ? select_kernel_l<4>(is_int, l2, stages, cl) : select_kernel_l<2>(is_int, l2, stages, cl);
+inline const void* select_kernel(bool is_int, bool l2, int cl, int eg, bool pair) {
+    return eg == 4 ? select_kernel_l<4>(is_int, l2, cl, pair) : select_kernel_l<2>(is_int, l2, cl, pair);
 }
 
 inline void make_map(TcState& st, CUtensorMap* map, const void* base, int dtype, uint64_t rows, uint32_t d, uint64_t pitch,
@@ -150,8 +158,11 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     const uint32_t cap = cap_for_k(a.k);
     const uint32_t kblocks = (a.d * es + BKB - 1) / BKB;
     int EG = st.epi_groups ? st.epi_groups : (kblocks <= 2 ? 4 : 2);
-    if (smem_bytes(cap, EG, 3) > 227 * 1024) EG = 2;
-    const int stages = stages_for(cap, EG);
+    // short rows are bound by the epilogue, and a pair's leader waits for the slower of two epilogues (measured on
+    // config E batched: 840 -> 620 TOP/s), so the pair form is for rows of more than two K blocks (MVF_TC_PAIR=2 forces it)
+    const bool pair = CL == 2 && (st.pair == 2 || (st.pair == 1 && kblocks > 2));
+    if (smem_bytes(cap, EG, 3, pair) > 227 * 1024) EG = 2;
+    const int stages = stages_for(cap, EG, pair);
 
     st.qprep.reserve((size_t)mtiles * BM * qpitch);
     st.qconst.reserve((size_t)a.nq * 4);
@@ -159,6 +170,11 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     st.lists.reserve((size_t)a.nq * chunks * EG * a.k * 8);
     st.gthr.reserve((size_t)mgroups * CL * BM * 4);
     TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mgroups * CL * BM * 4, stream));
+    const uint32_t sync_window = st.sync_window >= 0 ? (uint32_t)st.sync_window : (mgroups >= 8 ? 16u : 0u);
+    if (sync_window) {
+        st.progress.reserve((size_t)items * 4);
+        TC_CUDA_CHECK(cudaMemsetAsync(st.progress.p, 0, (size_t)items * 4, stream));
+    }
     uint64_t launches = 0;
     TC_CUDA_CHECK(cudaMemsetAsync(st.qprep.p, 0, (size_t)mtiles * BM * qpitch, stream));
     if (is_int) {
@@ -186,14 +202,17 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     const uint32_t fmt = a.dtype == k::DT_I8 ? 1u : 0u;     // kind::i8: 0 = unsigned, 1 = signed; kind::f16: 0 = F16
     const uint32_t cfmt = is_int ? 2u : 1u;                  // accumulator: S32 / F32
     p.l2_prefetch_tiles = (uint32_t)st.l2_prefetch;
-    p.idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    p.stages = (uint32_t)stages;
+    p.progress = (uint32_t*)st.progress.p; p.sync_window = sync_window;
+    // the pair form's instruction spans both CTAs: M = 256
+    p.idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
     if (a.dump) {
         st.dump.reserve((size_t)mtiles * BM * (size_t)ntiles * BN * 4);
         p.dump = (float*)st.dump.p;
     }
     const bool l2 = a.metric == k::M_L2;
-    const void* fn = select_kernel(is_int, l2, stages, (int)CL, EG);
-    const size_t smem = smem_bytes(cap, EG, stages);
+    const void* fn = select_kernel(is_int, l2, (int)CL, EG, pair);
+    const size_t smem = smem_bytes(cap, EG, stages, pair);
     TC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&map_q, (void*)&map_x, (void*)&p};
     cudaLaunchConfig_t cfg = {};
@@ -212,7 +231,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
 }
 
 inline void release(TcState& st) {
-    st.qprep.release(); st.qconst.release(); st.cand.release(); st.lists.release(); st.dump.release(); st.gthr.release();
+    st.qprep.release(); st.qconst.release(); st.cand.release(); st.lists.release(); st.dump.release(); st.gthr.release(); st.progress.release();
 }
 
 }  // namespace tc

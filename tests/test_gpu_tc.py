@@ -114,3 +114,28 @@ def test_ties_and_degenerate_queries_on_the_tensor_path(engine):
         gu.free()
     finally:
         engine.set_path(0)
+
+
+@pytest.mark.parametrize("env", [{"MVF_TC_PAIR": "2"}, {"MVF_TC_PAIR": "0"}, {"MVF_TC_CLUSTER": "1"},
+                                 {"MVF_TC_PAIR": "2", "MVF_TC_SYNC_WINDOW": "2"}, {"MVF_TC_PAIR": "0", "MVF_TC_SYNC_WINDOW": "1"}])
+def test_every_kernel_form_matches_oracle(env, monkeypatch):
+    # the knobs are read when an engine first uses the tensor path: CTA-pair MMAs (cta_group::2), multicast
+    # clusters, single CTAs, and the producer pacing, each forced on shapes that would not pick it by default
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    eng = mv.GpuEngine(0)
+    eng.set_path(2)
+    try:
+        for dtype, d, n in ((oracle.U8, 128, 40000), (oracle.I8, 320, 9000), (oracle.F16, 96, 30000)):
+            db = mv.synth_fill_host(dtype, 61, 0, n, d)
+            gs = eng.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+            q = mv.synth_fill_host(dtype, 62, 0, 300, d)
+            for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)):
+                ids, sc, isc = gs.search(q, 10, metric=metric)
+                assert eng.profile_read()["last_path"] == 2
+                qq = q.astype(np.float32) if dtype == oracle.F16 else q
+                check_batch(db, dtype, metric, qq[:8], 10, ids[:8], sc[:8], isc[:8])
+                check_batch(db, dtype, metric, qq[-4:], 10, ids[-4:], sc[-4:], isc[-4:])
+            gs.free()
+    finally:
+        eng.shutdown()
