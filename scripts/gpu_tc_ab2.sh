@@ -1,6 +1,9 @@
 #!/bin/bash
-VAR=${1}; A=${2}; B=${3}
-for rep in 1 2; do for V in $A $B; do
+# same-box A/B of a tensor-path knob on the three batched configs, no tests
+VAR=${1:-MVF_TC_SYNC_WINDOW}; shift
+for rep in 1 2; do for V in "$@"; do
 echo "== $VAR=$V (rep $rep)"
-env $VAR=$V timeout 600 python scripts/bench_summary.py C --steps 6 --warmup 3
+env $VAR=$V timeout 300 python scripts/bench_summary.py C --steps 6 --warmup 3
+env $VAR=$V timeout 300 python scripts/bench_summary.py D1024 --steps 6 --warmup 3 --rows 20000000
+env $VAR=$V timeout 300 python scripts/bench_summary.py E1024 --steps 6 --warmup 3 --rows 100000000
 done; done
