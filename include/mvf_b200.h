@@ -116,6 +116,22 @@ MVF_API int mvf_space_map_vector_range(const mvf_space* s, uint64_t start, uint6
  * set = row i deleted.  bitmap = NULL when the footer has none (the reference's builder never writes one,
  * src/builder.rs:486). */
 MVF_API int mvf_space_tombstones(const mvf_space* s, const void** bitmap, size_t* nbytes, uint64_t* deleted_count);
+/* TombstoneInfo{SortedList} (schema/types.fbs:35-39): ascending deleted row positions, u64 little-endian each (the
+ * schema leaves the element type open and nothing in the reference writes one: this is the definition our writer
+ * and reader share).  rows = NULL when the space has no list; the pointer is into the mmap and may be unaligned. */
+MVF_API int mvf_space_tombstone_list(const mvf_space* s, const uint64_t** rows, size_t* count, uint64_t* deleted_count);
+/* External ids: the block vector_ids_block_index names (schema/core.fbs:54; u64 LE per row, as
+ * src/builder.rs:257-271 serialises VectorSpaceBuilder.vector_ids).  ids = NULL when the footer says 0 = "use
+ * positions as IDs" (every file the reference's builder writes, src/builder.rs:483).  May be unaligned. */
+MVF_API int mvf_space_vector_ids(const mvf_space* s, const void** ids, size_t* count);
+/* Raw bytes of a metadata column (table MetadataColumn, schema/core.fbs:16-25; written by
+ * MvfBuilder::add_metadata_column, src/builder.rs:211-236; the reference reader only lists the names,
+ * src/reader.rs:132-143).  MVF_ERR_BUILD if there is no such column. */
+MVF_API int mvf_file_metadata_column(const mvf_file* f, const char* name, const void** bytes, size_t* nbytes, int* data_type);
+/* Pre-filter helper: evaluates lo <= column[i] <= hi for n values of `data_type`
+ * (Float32, Float16, Int8, UInt8, UInt32, UInt64) and SETS bit i of out_bitmap ((n+7)/8 bytes, LSB first) for the
+ * rows that FAIL, i.e. it produces exactly what mvf_gpu_space_set_row_mask expects. */
+MVF_API int mvf_filter_range_bitmap(const void* column, int data_type, uint64_t n, double lo, double hi, uint8_t* out_bitmap);
 /* rows the reference scan `for i in 0..space.total_vectors()` can actually visit:
  * min(total_vectors, block.size / (dimension*elem_size)) -- see DESIGN.md "f16 total_vectors" */
 MVF_API int mvf_space_scannable_vectors(const mvf_space* s, uint64_t* out);
@@ -141,6 +157,11 @@ MVF_API int mvf_builder_add_metadata_column(mvf_builder* b, const char* name, in
                                             const void* bytes, size_t nbytes);
 /* extension: attach a deletion bitmap to a space (written as TombstoneInfo{Bitmap} + one data block) */
 MVF_API int mvf_builder_set_tombstones(mvf_builder* b, const char* space, const void* bitmap, size_t nbytes);
+/* same, as TombstoneInfo{SortedList}: strictly ascending row positions (replaces a bitmap set earlier) */
+MVF_API int mvf_builder_set_tombstone_list(mvf_builder* b, const char* space, const uint64_t* rows, size_t count);
+/* VectorSpaceBuilder.vector_ids (src/builder.rs:61): one external u64 id per row already added to the space; written
+ * as its own data block and named by vector_ids_block_index.  MVF_ERR_DIMENSION_MISMATCH if count != rows. */
+MVF_API int mvf_builder_set_vector_ids(mvf_builder* b, const char* space, const uint64_t* ids, size_t count);
 /* MvfBuilder::build + BuiltMvf::save, src/builder.rs:241-308,404-411, src/io.rs:41-46.
  * Writes the correct total_vectors for every dtype (the reference halves it for Float16,
  * src/builder.rs:476). */
@@ -179,6 +200,13 @@ MVF_API void mvf_gpu_space_free(mvf_gpu_space* s);
  * a key mask inside the scan / tensor-core epilogues.  NULL clears.  mvf_gpu_space_upload applies the file's own
  * tombstone bitmap automatically. */
 MVF_API int mvf_gpu_space_set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits);
+/* The space's own deletions, kept apart from the filter above: every search excludes (tombstones OR row mask).
+ * mvf_gpu_space_upload sets this from the file's TombstoneInfo (bitmap or sorted list).  NULL clears. */
+MVF_API int mvf_gpu_space_set_tombstones(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits);
+/* External ids (vector_ids_block_index): a table of global_n u64 ids, one per GLOBAL row, kept in HBM on every
+ * rank; searches then report ids[row] instead of the row position (ties are still broken by position, and
+ * mvf_gpu_space_get_vectors still takes positions).  NULL clears.  mvf_gpu_space_upload applies the file's table. */
+MVF_API int mvf_gpu_space_set_ids(mvf_gpu_space* s, const uint64_t* ids, uint64_t count);
 MVF_API int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base,
                                uint64_t* global_n, uint32_t* dimension, int* data_type, int* metric);
 /* how the rows got to HBM: path 1 = cudaHostRegister'd mapping, 2 = pinned staging, 0 = generated */

@@ -138,6 +138,14 @@ _SIGS = {
     "mvf_gpu_space_set_row_mask": [_P, _P, _U64],
     "mvf_space_tombstones": [_P, _c.POINTER(_P), _c.POINTER(_SZ), _c.POINTER(_U64)],
     "mvf_builder_set_tombstones": [_P, _c.c_char_p, _P, _SZ],
+    "mvf_builder_set_tombstone_list": [_P, _c.c_char_p, _P, _SZ],
+    "mvf_builder_set_vector_ids": [_P, _c.c_char_p, _P, _SZ],
+    "mvf_space_tombstone_list": [_P, _c.POINTER(_P), _c.POINTER(_SZ), _c.POINTER(_U64)],
+    "mvf_space_vector_ids": [_P, _c.POINTER(_P), _c.POINTER(_SZ)],
+    "mvf_file_metadata_column": [_P, _c.c_char_p, _c.POINTER(_P), _c.POINTER(_SZ), _c.POINTER(_INT)],
+    "mvf_filter_range_bitmap": [_P, _INT, _U64, _c.c_double, _c.c_double, _P],
+    "mvf_gpu_space_set_tombstones": [_P, _P, _U64],
+    "mvf_gpu_space_set_ids": [_P, _P, _U64],
     "mvf_gpu_space_checksum": [_P, _c.POINTER(_U32), _c.POINTER(_c.c_double)],
     "mvf_gpu_space_verify_checksum": [_P, _P],
     "mvf_gpu_space_get_vectors": [_P, _P, _U32, _INT, _P],
@@ -151,6 +159,17 @@ _SIGS = {
 for _name, _args in _SIGS.items():
     getattr(_lib, _name).restype = _INT
     getattr(_lib, _name).argtypes = _args
+
+
+def filter_range_bitmap(column, data_type, lo, hi):
+    """Boolean array, True = row FAILS lo <= value <= hi (the exclusion convention of GpuSpace.set_row_mask).
+    column: raw bytes or a numpy array of the column's values."""
+    raw = column.tobytes() if isinstance(column, np.ndarray) else bytes(column)
+    es = {0: 4, 1: 2, 2: 1, 3: 1, 4: 4, 5: 8}[int(data_type)]
+    n = len(raw) // es
+    out = np.zeros((n + 7) // 8, dtype=np.uint8)
+    _check(_lib.mvf_filter_range_bitmap(raw, int(data_type), n, float(lo), float(hi), out.ctypes.data_as(_P)))
+    return np.unpackbits(out, bitorder="little")[:n].astype(bool)
 
 
 def _check(rc):
@@ -255,6 +274,22 @@ class VectorSpace:
         raw = np.frombuffer(_c.string_at(ptr.value, n.value), dtype=np.uint8)
         return np.unpackbits(raw, bitorder="little").astype(bool)
 
+    def tombstone_list(self):
+        """Deleted row positions of the footer's TombstoneInfo{SortedList} (uint64 array), or None."""
+        ptr, n, cnt = _P(), _SZ(), _U64()
+        _check(_lib.mvf_space_tombstone_list(self._h, _c.byref(ptr), _c.byref(n), _c.byref(cnt)))
+        if not ptr.value:
+            return None
+        return np.frombuffer(_c.string_at(ptr.value, n.value * 8), dtype="<u8").copy()
+
+    def vector_ids(self):
+        """External ids (vector_ids_block_index, schema/core.fbs:54) as a uint64 array, or None = positions."""
+        ptr, n = _P(), _SZ()
+        _check(_lib.mvf_space_vector_ids(self._h, _c.byref(ptr), _c.byref(n)))
+        if not ptr.value:
+            return None
+        return np.frombuffer(_c.string_at(ptr.value, n.value * 8), dtype="<u8").copy()
+
     def get_vector(self, index):                          # vector_space.rs:101-142
         ptr, n = _P(), _SZ()
         _check(_lib.mvf_space_get_vector(self._h, index, _c.byref(ptr), _c.byref(n)))
@@ -340,6 +375,12 @@ class MvfReader:
             out.append(s.value.decode())
         return out
 
+    def metadata_column(self, name):
+        """(raw bytes, DataType) of a metadata column (schema/core.fbs:16-25)."""
+        ptr, n, dt = _P(), _SZ(), _INT()
+        _check(_lib.mvf_file_metadata_column(self._h, name.encode(), _c.byref(ptr), _c.byref(n), _c.byref(dt)))
+        return _c.string_at(ptr.value, n.value), DataType(dt.value)
+
     def validate(self):
         _check(_lib.mvf_file_validate(self._h))
 
@@ -385,6 +426,16 @@ class MvfBuilder:
         """deleted: boolean array over the space's rows; written as TombstoneInfo{Bitmap}."""
         bits = np.packbits(np.asarray(deleted, dtype=bool), bitorder="little").tobytes()
         _check(_lib.mvf_builder_set_tombstones(self._h, space.encode(), bits, len(bits)))
+
+    def set_tombstone_list(self, space, rows):
+        """rows: strictly ascending deleted positions; written as TombstoneInfo{SortedList} (u64 LE)."""
+        a = np.ascontiguousarray(rows, dtype=np.uint64)
+        _check(_lib.mvf_builder_set_tombstone_list(self._h, space.encode(), a.ctypes.data_as(_P), a.size))
+
+    def set_vector_ids(self, space, ids):
+        """ids: one external uint64 id per row of the space (VectorSpaceBuilder.vector_ids, src/builder.rs:61)."""
+        a = np.ascontiguousarray(ids, dtype=np.uint64)
+        _check(_lib.mvf_builder_set_vector_ids(self._h, space.encode(), a.ctypes.data_as(_P), a.size))
 
     def add_metadata_column(self, name, data_type, data):
         b = bytes(data)
@@ -510,6 +561,22 @@ class GpuSpace:
             return
         bits = np.packbits(np.asarray(excluded, dtype=bool), bitorder="little")
         _check(_lib.mvf_gpu_space_set_row_mask(self._h, bits.ctypes.data_as(_P), len(excluded)))
+
+    def set_tombstones(self, deleted):
+        """deleted: boolean array over GLOBAL rows, or None; kept apart from set_row_mask (searches exclude the union)."""
+        if deleted is None:
+            _check(_lib.mvf_gpu_space_set_tombstones(self._h, None, 0))
+            return
+        bits = np.packbits(np.asarray(deleted, dtype=bool), bitorder="little")
+        _check(_lib.mvf_gpu_space_set_tombstones(self._h, bits.ctypes.data_as(_P), len(deleted)))
+
+    def set_ids(self, ids):
+        """ids: uint64 array, one external id per GLOBAL row (reported by searches instead of positions), or None."""
+        if ids is None:
+            _check(_lib.mvf_gpu_space_set_ids(self._h, None, 0))
+            return
+        a = np.ascontiguousarray(ids, dtype=np.uint64)
+        _check(_lib.mvf_gpu_space_set_ids(self._h, a.ctypes.data_as(_P), a.size))
 
     def checksum(self):
         """CRC-32/IEEE of the resident rows, computed on the device.  Returns (crc, kernel_ms)."""

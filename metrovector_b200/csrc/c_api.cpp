@@ -93,6 +93,56 @@ int mvf_space_tombstones(const mvf_space* s, const void** bitmap, size_t* nbytes
         if (deleted_count) *deleted_count = s->vs.deleted_count();
     });
 }
+int mvf_space_tombstone_list(const mvf_space* s, const uint64_t** rows, size_t* count, uint64_t* deleted_count) {
+    return guard([&] {
+        size_t n = 0;
+        const uint8_t* p = s->vs.tombstone_list(&n);
+        if (rows) *rows = (const uint64_t*)p;            // blocks of u64 start at arbitrary file offsets: read with memcpy if alignment matters
+        if (count) *count = n;
+        if (deleted_count) *deleted_count = s->vs.deleted_count();
+    });
+}
+int mvf_space_vector_ids(const mvf_space* s, const void** ids, size_t* count) {
+    return guard([&] {
+        size_t n = 0;
+        const uint8_t* p = s->vs.vector_ids(&n);
+        if (ids) *ids = p;
+        if (count) *count = n;
+    });
+}
+int mvf_file_metadata_column(const mvf_file* f, const char* name, const void** bytes, size_t* nbytes, int* data_type) {
+    return guard([&] {
+        size_t n = 0; DataType dt = DataType::UInt8;
+        const uint8_t* p = f->r->metadata_column(name ? name : "", &n, &dt);
+        if (bytes) *bytes = p;
+        if (nbytes) *nbytes = n;
+        if (data_type) *data_type = (int)dt;
+    });
+}
+// Pre-filter helper: bit i of out_bitmap (LSB first) is SET (= row excluded, the convention of
+// mvf_gpu_space_set_row_mask) when value i of the column lies outside [lo, hi].
+int mvf_filter_range_bitmap(const void* column, int data_type, uint64_t n, double lo, double hi, uint8_t* out_bitmap) {
+    return guard([&] {
+        if (!column || !out_bitmap) throw MvfError::build_error("null argument");
+        const uint8_t* c = (const uint8_t*)column;
+        std::memset(out_bitmap, 0, (size_t)((n + 7) / 8));
+        auto run = [&](auto load) {
+            for (uint64_t i = 0; i < n; i++) {
+                const double v = load(i);
+                if (!(v >= lo && v <= hi)) out_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+            }
+        };
+        switch ((DataType)data_type) {
+            case DataType::Float32: run([&](uint64_t i) { float v; std::memcpy(&v, c + 4 * i, 4); return (double)v; }); break;
+            case DataType::Float16: run([&](uint64_t i) { uint16_t h; std::memcpy(&h, c + 2 * i, 2); return (double)f16_to_f32(h); }); break;
+            case DataType::Int8: run([&](uint64_t i) { return (double)(int8_t)c[i]; }); break;
+            case DataType::UInt8: run([&](uint64_t i) { return (double)c[i]; }); break;
+            case DataType::UInt32: run([&](uint64_t i) { uint32_t v; std::memcpy(&v, c + 4 * i, 4); return (double)v; }); break;
+            case DataType::UInt64: run([&](uint64_t i) { uint64_t v; std::memcpy(&v, c + 8 * i, 8); return (double)v; }); break;
+            default: throw MvfError::build_error("Unsupported metadata data type for a range filter");
+        }
+    });
+}
 int mvf_space_scannable_vectors(const mvf_space* s, uint64_t* out) { return guard([&] { *out = s->vs.scannable_vectors(); }); }
 
 int mvf_builder_new(mvf_builder** out) { return guard([&] { *out = new mvf_builder(); }); }
@@ -116,6 +166,12 @@ int mvf_builder_add_metadata_column(mvf_builder* b, const char* name, int data_t
 }
 int mvf_builder_set_tombstones(mvf_builder* b, const char* space, const void* bitmap, size_t nbytes) {
     return guard([&] { b->b.set_tombstones(space, bitmap, nbytes); });
+}
+int mvf_builder_set_tombstone_list(mvf_builder* b, const char* space, const uint64_t* rows, size_t count) {
+    return guard([&] { b->b.set_tombstone_list(space, rows, count); });
+}
+int mvf_builder_set_vector_ids(mvf_builder* b, const char* space, const uint64_t* ids, size_t count) {
+    return guard([&] { b->b.set_vector_ids(space, ids, count); });
 }
 int mvf_builder_save(mvf_builder* b, const char* path) { return guard([&] { b->b.save(path); }); }
 

@@ -117,8 +117,10 @@ struct mvf_gpu_space {
     unsigned char* rows = nullptr;
     float* norm = nullptr;
     float* sq = nullptr;
-    uint32_t* mask = nullptr;  // optional row mask (bit set = row excluded): tombstones / pre-filters
+    uint32_t* mask = nullptr;  // optional row mask (bit set = row excluded): tombstones OR pre-filter, what the kernels read
     uint64_t masked_rows = 0;
+    std::vector<uint32_t> mask_part[2];   // host copies of the two components, local rows: [0] tombstones, [1] filter
+    uint64_t* ext_ids = nullptr;          // optional external id per GLOBAL row (vector_ids_block_index)
     int upload_path = 0;       // 0 none/synthetic, 1 cudaHostRegister'd mapping, 2 pinned staging
     double upload_seconds = 0.0;
     std::string upload_note;   // why the in-place registration was not used, if it was not
@@ -321,6 +323,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
         mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 1; mp.qconst = r.qconst;
         mp.out_packed = multi ? packed_local : nullptr;
         mp.out_ids = multi ? nullptr : d_ids; mp.out_scores = multi ? nullptr : d_scores; mp.out_iscores = multi ? nullptr : d_iscores;
+        mp.ext_ids = s->ext_ids;
         launch_merge(g, mp, nq);
         tc_keys = true; tc_qconst = r.qconst;
         done = true;
@@ -352,6 +355,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
             mp.out_ids = multi ? nullptr : d_ids + o;
             mp.out_scores = multi ? nullptr : (d_scores ? d_scores + o : nullptr);
             mp.out_iscores = multi ? nullptr : (d_iscores ? d_iscores + o : nullptr);
+            mp.ext_ids = s->ext_ids;
             launch_merge(g, mp, (uint32_t)NQ);
             q0 += (uint32_t)NQ;
         }
@@ -366,6 +370,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
         mp.in = (const u64*)g->gathered.p; mp.q_stride = kk; mp.list_stride = cnt; mp.nlists = (uint32_t)g->world; mp.k = kk;
         mp.id_add = 0; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = tc_keys ? 1 : 0; mp.qconst = tc_qconst;
         mp.out_packed = nullptr; mp.out_ids = d_ids; mp.out_scores = d_scores; mp.out_iscores = d_iscores;
+        mp.ext_ids = s->ext_ids;
         launch_merge(g, mp, nq);
     }
 }
@@ -528,27 +533,64 @@ void upload_rows(mvf_gpu_space* s, const unsigned char* src, uint64_t nrows, siz
 
 // Row mask: bit i (LSB first) of `bitmap`, indexed by GLOBAL row, set = row i never appears in a result.
 // The shard's bits are re-based to local rows on the host and kept as 32-bit words on the device.
-void set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
+// Two components are kept apart on the host -- the space's deletions (part 0) and the caller's filter (part 1) --
+// and their union is what the kernels see, so a filter never resurrects a deleted row.
+void set_mask_part(mvf_gpu_space* s, int part, const uint8_t* bitmap, uint64_t nbits) {
     mvf_gpu* g = s->g;
     CUDA_CHECK(cudaSetDevice(g->device));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    if (!bitmap || nbits == 0) { cudaFree(s->mask); s->mask = nullptr; s->masked_rows = 0; return; }
     const size_t words = (size_t)((s->local_n + k::kPadRows + 31) / 32);
-    std::vector<uint32_t> local(words, 0);
+    std::vector<uint32_t>& mine = s->mask_part[part];
+    if (!bitmap || nbits == 0) {
+        mine.clear(); mine.shrink_to_fit();
+    } else {
+        mine.assign(words, 0);
+        auto bit = [&](uint64_t gb) -> uint32_t { return gb < nbits ? (bitmap[gb >> 3] >> (gb & 7)) & 1u : 0u; };
+        for (uint64_t w = 0; w * 32 < s->local_n; w++) {          // 32 local rows per word, any bit offset in the global bitmap
+            const uint64_t g0 = s->row_base + w * 32;
+            const uint64_t lim = std::min<uint64_t>(32, s->local_n - w * 32);
+            uint32_t v = 0;
+            if (g0 + 40 <= nbits) {                                // whole window inside the bitmap: one unaligned 5-byte read
+                uint64_t raw = 0;
+                std::memcpy(&raw, bitmap + (g0 >> 3), 5);            // bits g0 .. g0+39 exist, so these 5 bytes do
+                v = (uint32_t)(raw >> (g0 & 7));
+                if (lim < 32) v &= (1u << lim) - 1u;
+            } else {
+                for (uint64_t b = 0; b < lim; b++) v |= bit(g0 + b) << b;
+            }
+            mine[w] = v;
+        }
+    }
+    const std::vector<uint32_t>& a = s->mask_part[0];
+    const std::vector<uint32_t>& b = s->mask_part[1];
+    if (a.empty() && b.empty()) { cudaFree(s->mask); s->mask = nullptr; s->masked_rows = 0; return; }
+    std::vector<uint32_t> both(words, 0);
     uint64_t masked = 0;
-    for (uint64_t i = 0; i < s->local_n; i++) {
-        const uint64_t gbit = s->row_base + i;
-        if (gbit < nbits && ((bitmap[gbit >> 3] >> (gbit & 7)) & 1)) { local[i >> 5] |= 1u << (i & 31); masked++; }
+    for (size_t w = 0; w < words; w++) {
+        both[w] = (a.empty() ? 0u : a[w]) | (b.empty() ? 0u : b[w]);
+        masked += (uint64_t)__builtin_popcount(both[w]);
     }
     if (!s->mask) CUDA_CHECK(cudaMalloc((void**)&s->mask, words * 4));
-    CUDA_CHECK(cudaMemcpy(s->mask, local.data(), words * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(s->mask, both.data(), words * 4, cudaMemcpyHostToDevice));
     s->masked_rows = masked;
+}
+void set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) { set_mask_part(s, 1, bitmap, nbits); }
+
+// External ids, one per GLOBAL row, replicated on every rank: the merged candidates carry global positions.
+void set_ids(mvf_gpu_space* s, const void* ids, uint64_t count) {
+    mvf_gpu* g = s->g;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    if (!ids || count == 0) { cudaFree(s->ext_ids); s->ext_ids = nullptr; return; }
+    if (count < s->global_n) throw MvfError::dimension_mismatch(s->global_n, count);
+    if (!s->ext_ids) CUDA_CHECK(cudaMalloc((void**)&s->ext_ids, (size_t)s->global_n * 8));
+    CUDA_CHECK(cudaMemcpy(s->ext_ids, ids, (size_t)s->global_n * 8, cudaMemcpyHostToDevice));
 }
 
 void free_space(mvf_gpu_space* s) {
     if (!s) return;
     cudaSetDevice(s->g->device);
-    cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask);
+    cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask); cudaFree(s->ext_ids);
     delete s;
 }
 
@@ -668,8 +710,20 @@ int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* sp, mvf_gpu_space** out) {
                 CUDA_CHECK(cudaStreamSynchronize(g->stream));
                 // TombstoneInfo{Bitmap} in the footer (schema/core.fbs:34-39): deleted rows never compete
                 size_t tb = 0;
-                if (const uint8_t* tomb = vs.tombstone_bitmap(&tb)) set_row_mask(s, tomb, (uint64_t)tb * 8);
+                if (const uint8_t* tomb = vs.tombstone_bitmap(&tb)) {
+                    set_mask_part(s, 0, tomb, (uint64_t)tb * 8);
+                } else if (const uint8_t* lst = vs.tombstone_list(&tb)) {   // TombstoneInfo{SortedList}: positions -> bitmap
+                    std::vector<uint8_t> bm((size_t)((n + 7) / 8), 0);
+                    for (size_t i = 0; i < tb; i++) {
+                        uint64_t r; std::memcpy(&r, lst + 8 * i, 8);
+                        if (r < n) bm[r >> 3] |= (uint8_t)(1u << (r & 7));
+                    }
+                    set_mask_part(s, 0, bm.data(), n);
+                }
             }
+            // external ids (vector_ids_block_index != 0): reported instead of positions
+            size_t nid = 0;
+            if (const uint8_t* ids = vs.vector_ids(&nid)) set_ids(s, ids, (uint64_t)nid);
         } catch (...) { free_space(s); throw; }
         *out = s;
     });
@@ -719,6 +773,12 @@ int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t glob
 
 void mvf_gpu_space_free(mvf_gpu_space* s) { free_space(s); }
 
+int mvf_gpu_space_set_tombstones(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
+    return guard([&] { set_mask_part(s, 0, bitmap, nbits); });
+}
+int mvf_gpu_space_set_ids(mvf_gpu_space* s, const uint64_t* ids, uint64_t count) {
+    return guard([&] { set_ids(s, ids, count); });
+}
 int mvf_gpu_space_set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
     return guard([&] { set_row_mask(s, bitmap, nbits); });
 }

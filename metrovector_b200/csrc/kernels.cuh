@@ -152,6 +152,7 @@ struct MergeParams {
     int metric, dtype;
     int tc_mode;              // keys hold K2's ranking value (tc_kernels.cuh); decode with qconst
     const float* qconst;      // per query: 1/|q| (cosine), |q|^2 (L2; int32 bits for integer spaces)
+    const uint64_t* ext_ids = nullptr;   // optional external id per GLOBAL row (vector_ids_block_index, schema/core.fbs:54): reported instead of the position
 };
 
 // decode one merged candidate into the caller's output arrays
@@ -161,7 +162,7 @@ __device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, ui
     const size_t o = (size_t)q * p.k + j;
     if (p.out_packed) p.out_packed[o] = v;
     const uint32_t key = (uint32_t)(v >> 32);
-    if (p.out_ids) p.out_ids[o] = valid ? (uint64_t)(uint32_t)v : ~0ull;
+    if (p.out_ids) p.out_ids[o] = valid ? (p.ext_ids ? p.ext_ids[(uint32_t)v] : (uint64_t)(uint32_t)v) : ~0ull;
     const bool int_score = (p.dtype == DT_I8 || p.dtype == DT_U8) && p.metric != M_COS;
     if (int_score) {
         int s = (int)(key ^ 0x80000000u);

@@ -148,6 +148,23 @@ void MvfBuilder::add_metadata_column(const std::string& name, DataType dt, const
 void MvfBuilder::set_tombstones(const std::string& space, const void* bitmap, size_t nbytes) {
     VectorSpaceBuilder& s = find(space);
     s.tombstones.assign((const uint8_t*)bitmap, (const uint8_t*)bitmap + nbytes);
+    s.tombstone_list.clear();
+}
+
+void MvfBuilder::set_tombstone_list(const std::string& space, const uint64_t* rows, size_t count) {
+    VectorSpaceBuilder& s = find(space);
+    for (size_t i = 1; i < count; i++)
+        if (rows[i] <= rows[i - 1]) throw MvfError::build_error("Tombstone list must be strictly ascending");
+    s.tombstone_list.assign((const uint8_t*)rows, (const uint8_t*)rows + count * 8);   // little-endian host
+    s.tombstones.clear();
+}
+
+void MvfBuilder::set_vector_ids(const std::string& space, const uint64_t* ids, size_t count) {
+    VectorSpaceBuilder& s = find(space);
+    size_t es = element_size(s.data_type);
+    uint64_t total = (s.dimension && es) ? s.vectors.size() / ((uint64_t)s.dimension * es) : 0;
+    if (count != total) throw MvfError::dimension_mismatch(total, count);
+    s.vector_ids.assign((const uint8_t*)ids, (const uint8_t*)ids + count * 8);
 }
 
 std::vector<uint8_t> MvfBuilder::to_bytes() const {
@@ -163,11 +180,16 @@ std::vector<uint8_t> MvfBuilder::to_bytes() const {
     for (const auto& s : spaces_) add_block(s.vectors);
     for (const auto& c : columns_) add_block(c.data);
     // deletion bitmaps go after the metadata columns (the reference never emits any, so the position is ours)
-    std::vector<uint32_t> tomb_block(spaces_.size(), 0);
+    std::vector<uint32_t> tomb_block(spaces_.size(), 0), ids_block(spaces_.size(), 0);
     {
         uint32_t next = (uint32_t)(spaces_.size() + columns_.size());
         for (size_t i = 0; i < spaces_.size(); i++)
             if (!spaces_[i].tombstones.empty()) { add_block(spaces_[i].tombstones); tomb_block[i] = next++; }
+            else if (!spaces_[i].tombstone_list.empty()) { add_block(spaces_[i].tombstone_list); tomb_block[i] = next++; }
+        // external ids last: the reference's build() would interleave them after each vector block (builder.rs:257-271)
+        // but then points vectors_block_index at the wrong block (:481); any position is legal through the index
+        for (size_t i = 0; i < spaces_.size(); i++)
+            if (!spaces_[i].vector_ids.empty()) { add_block(spaces_[i].vector_ids); ids_block[i] = next++; }
     }
 
     FbEncoder fb;
@@ -181,17 +203,19 @@ std::vector<uint8_t> MvfBuilder::to_bytes() const {
         uint64_t total = (s.dimension && es) ? s.vectors.size() / ((uint64_t)s.dimension * es) : 0;
         size_t tomb = 0;
         if (tomb_block[i]) {
-            uint64_t deleted = 0;
+            const bool list = s.tombstones.empty();
+            uint64_t deleted = list ? s.tombstone_list.size() / 8 : 0;
             for (uint8_t byte : s.tombstones) deleted += (uint64_t)__builtin_popcount(byte);
             fb.start(3);
             fb.slot<uint64_t>(2, deleted, 0);
             fb.slot<uint32_t>(1, tomb_block[i], 0);
-            fb.slot<uint8_t>(0, 1, 0);                        // TombstoneFormat::Bitmap
+            fb.slot<uint8_t>(0, list ? 2 : 1, 0);             // TombstoneFormat::Bitmap / SortedList (schema/types.fbs:35-39)
             tomb = fb.end();
         }
         fb.start(12);
         fb.slot<uint64_t>(2, total, 0);
         fb.slot_off(11, tomb);
+        fb.slot<uint32_t>(9, ids_block[i], 0);               // vector_ids_block_index, 0 = positions
         fb.slot_off(8, flat);
         fb.slot<uint32_t>(6, (uint32_t)i, 0);
         fb.slot<uint32_t>(1, s.dimension, 0);

@@ -123,7 +123,13 @@ public:
     uint64_t scannable_vectors() const;
     // deletion bitmap (bit i, LSB first, = row i deleted) if the footer carries TombstoneInfo{Bitmap}; nullptr otherwise
     const uint8_t* tombstone_bitmap(size_t* nbytes) const;
+    // TombstoneInfo{SortedList}: ascending deleted row positions, u64 little-endian each (the schema leaves the element
+    // type open and the reference never writes one; this is the definition both our writer and reader use)
+    const uint8_t* tombstone_list(size_t* count) const;
     uint64_t deleted_count() const;
+    // external ids (vector_ids_block_index, schema/core.fbs:54; u64 LE per row like src/builder.rs:257-271 serialises
+    // them): nullptr when the footer says 0 = "use positions as IDs"
+    const uint8_t* vector_ids(size_t* count) const;
     const MvfReader* reader() const { return reader_; }
 private:
     const SpaceInfo& info() const;
@@ -146,6 +152,9 @@ public:
     uint64_t file_size() const { return size_; }                      // :122
     bool has_metadata() const { return has_metadata_; }               // :127
     const std::vector<std::string>& metadata_column_names() const { return metadata_names_; }   // :132-143
+    // raw bytes of a metadata column (table MetadataColumn, schema/core.fbs:16-25; the reference reader stops at
+    // the names): what a pre-filter is evaluated on.  Throws VectorSpaceNotFound-style Build error if absent.
+    const uint8_t* metadata_column(const std::string& name, size_t* nbytes, DataType* dt) const;
     void validate() const;                                            // :149-162
     void validate_with_checksum() const;                              // :172-221 (intent)
     const uint8_t* data() const { return map_; }
@@ -162,6 +171,8 @@ private:
     std::vector<SpaceInfo> spaces_;
     std::vector<DataBlock> blocks_;
     std::vector<std::string> metadata_names_;
+    std::vector<uint32_t> metadata_blocks_;
+    std::vector<uint8_t> metadata_types_;
 };
 using MvfFile = MvfReader;
 
@@ -180,6 +191,8 @@ struct VectorSpaceBuilder {      // src/builder.rs:64-76
     DataType data_type = DataType::Float32;
     std::vector<uint8_t> vectors;
     std::vector<uint8_t> tombstones;       // deletion bitmap, empty = none (extension: the reference never writes one)
+    std::vector<uint8_t> tombstone_list;   // or: ascending deleted positions, u64 LE (TombstoneFormat::SortedList)
+    std::vector<uint8_t> vector_ids;       // u64 LE external id per row (src/builder.rs:61,257-271), empty = positions
 };
 
 class MvfBuilder {               // src/builder.rs:93-98
@@ -190,6 +203,8 @@ public:
     void add_vectors_raw(const std::string& space, const void* rows, size_t nrows, uint32_t dimension);
     void add_metadata_column(const std::string& name, DataType dt, const void* bytes, size_t n);       // :211-236
     void set_tombstones(const std::string& space, const void* bitmap, size_t nbytes);   // TombstoneInfo{Bitmap}, schema/core.fbs:34-39
+    void set_tombstone_list(const std::string& space, const uint64_t* rows, size_t count);   // TombstoneInfo{SortedList}
+    void set_vector_ids(const std::string& space, const uint64_t* ids, size_t count);   // VectorSpaceBuilder.vector_ids, src/builder.rs:61
     std::vector<uint8_t> to_bytes() const;      // build() + BuiltMvf::to_bytes, :241-308,417-558
     void save(const std::string& path) const;   // BuiltMvf::save + MvfWriter::write, io.rs:41-46
 private:

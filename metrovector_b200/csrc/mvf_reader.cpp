@@ -203,6 +203,8 @@ void MvfReader::parse_footer(const uint8_t* footer, size_t len) {
             size_t p = md + 4 + (size_t)i * 4;
             Table t(&b, p + b.rd<uint32_t>(p));
             metadata_names_.push_back(t.str(0, true));
+            metadata_types_.push_back(t.scalar<uint8_t>(1, 0));
+            metadata_blocks_.push_back(t.scalar<uint32_t>(2, 0));
         }
     }
 }
@@ -342,19 +344,55 @@ uint64_t VectorSpace::scannable_vectors() const {
 
 uint64_t VectorSpace::deleted_count() const { return info().deleted_count; }
 
+// bounds-checked view of an auxiliary block (tombstones, ids) named by index in the manifest
+static const uint8_t* aux_block(const MvfReader* r, uint32_t index, const char* what, size_t* nbytes) {
+    const auto& blocks = r->blocks();
+    if (index >= blocks.size()) throw MvfError::corrupted_data(std::string("Invalid ") + what + " block index");
+    const DataBlock& blk = blocks[index];
+    uint64_t start = 4 + blk.offset;
+    if (start > r->file_size() || blk.size > r->file_size() - start)
+        throw MvfError::corrupted_data("Block extends beyond file: offset=" + std::to_string(blk.offset) + ", size=" +
+                                       std::to_string(blk.size) + ", file_size=" + std::to_string(r->file_size()));
+    *nbytes = (size_t)blk.size;
+    return r->data() + start;
+}
+
+const uint8_t* MvfReader::metadata_column(const std::string& name, size_t* nbytes, DataType* dt) const {
+    for (size_t i = 0; i < metadata_names_.size(); i++) {
+        if (metadata_names_[i] != name) continue;
+        if (dt) *dt = (DataType)metadata_types_[i];
+        return aux_block(this, metadata_blocks_[i], "metadata column", nbytes);
+    }
+    throw MvfError::build_error("Metadata column '" + name + "' not found");
+}
+
 const uint8_t* VectorSpace::tombstone_bitmap(size_t* nbytes) const {
     *nbytes = 0;
     const SpaceInfo& si = info();
     if (si.tombstone_format != 1 || si.tombstone_block_index == 0) return nullptr;
-    const auto& blocks = reader_->blocks();
-    if (si.tombstone_block_index >= blocks.size()) throw MvfError::corrupted_data("Invalid tombstone block index");
-    const DataBlock& blk = blocks[si.tombstone_block_index];
-    uint64_t start = 4 + blk.offset;
-    if (start > reader_->file_size() || blk.size > reader_->file_size() - start)
-        throw MvfError::corrupted_data("Block extends beyond file: offset=" + std::to_string(blk.offset) + ", size=" +
-                                       std::to_string(blk.size) + ", file_size=" + std::to_string(reader_->file_size()));
-    *nbytes = (size_t)blk.size;
-    return reader_->data() + start;
+    return aux_block(reader_, si.tombstone_block_index, "tombstone", nbytes);
+}
+
+const uint8_t* VectorSpace::tombstone_list(size_t* count) const {
+    *count = 0;
+    const SpaceInfo& si = info();
+    if (si.tombstone_format != 2 || si.tombstone_block_index == 0) return nullptr;
+    size_t nb = 0;
+    const uint8_t* p = aux_block(reader_, si.tombstone_block_index, "tombstone", &nb);
+    if (nb % 8) throw MvfError::corrupted_data("Tombstone list is not a whole number of 64-bit positions");
+    *count = nb / 8;
+    return p;
+}
+
+const uint8_t* VectorSpace::vector_ids(size_t* count) const {
+    *count = 0;
+    const SpaceInfo& si = info();
+    if (si.vector_ids_block_index == 0) return nullptr;              // 0 = use positions as IDs (schema/core.fbs:54)
+    size_t nb = 0;
+    const uint8_t* p = aux_block(reader_, si.vector_ids_block_index, "vector ids", &nb);
+    if (nb / 8 < scannable_vectors()) throw MvfError::corrupted_data("Vector id block is shorter than the vector space");
+    *count = nb / 8;
+    return p;
 }
 
 // ---- Vector ------------------------------------------------------------------------------------

@@ -155,14 +155,24 @@ def build_mvf(spaces, metadata_columns=(), string_heap=b"", format_version=1,
         blocks.append(_data_block(off, len(d), 0, 0, zlib.crc32(d) & 0xFFFFFFFF))
         payload += d
         off += len(d)
-    tomb_block = {}
+    tomb_block, ids_block = {}, {}
     for i, sp in enumerate(spaces):      # deletion bitmaps after the metadata columns (position is ours: the reference writes none)
         tb = sp.get("tombstones")
+        if not tb and sp.get("tombstone_list") is not None and len(sp["tombstone_list"]):
+            tb = struct.pack("<%dQ" % len(sp["tombstone_list"]), *sp["tombstone_list"])   # TombstoneFormat::SortedList, u64 LE
         if tb:
             blocks.append(_data_block(off, len(tb), 0, 0, zlib.crc32(tb) & 0xFFFFFFFF))
             payload += tb
             off += len(tb)
             tomb_block[i] = len(blocks) - 1
+    for i, sp in enumerate(spaces):      # external ids, u64 LE per row (src/builder.rs:257-271), after the tombstones
+        ids = sp.get("vector_ids")
+        if ids is not None and len(ids):
+            ib = struct.pack("<%dQ" % len(ids), *ids)
+            blocks.append(_data_block(off, len(ib), 0, 0, zlib.crc32(ib) & 0xFFFFFFFF))
+            payload += ib
+            off += len(ib)
+            ids_block[i] = len(blocks) - 1
     heap_index = 0
     if string_heap:
         blocks.append(_data_block(off, len(string_heap), 0, 0, zlib.crc32(string_heap) & 0xFFFFFFFF))
@@ -182,16 +192,17 @@ def build_mvf(spaces, metadata_columns=(), string_heap=b"", format_version=1,
             total = (len(sp["data"]) // (dim * es)) if dim else 0
         tomb = None
         if i in tomb_block:
-            deleted = sum(bin(x).count("1") for x in sp["tombstones"])
+            is_list = not sp.get("tombstones")
+            deleted = len(sp["tombstone_list"]) if is_list else sum(bin(x).count("1") for x in sp["tombstones"])
             b.start_table(3)
             b.slot_scalar(2, "Q", deleted, 0)
             b.slot_scalar(1, "I", tomb_block[i], 0)
-            b.slot_scalar(0, "B", 1, 0)            # TombstoneFormat::Bitmap
+            b.slot_scalar(0, "B", 2 if is_list else 1, 0)   # TombstoneFormat::Bitmap / SortedList
             tomb = b.end_table()
         b.start_table(12)
         b.slot_scalar(2, "Q", total, 0)
         b.slot_offset(11, tomb)
-        b.slot_scalar(9, "I", 0, 0)
+        b.slot_scalar(9, "I", ids_block.get(i, 0), 0)   # vector_ids_block_index, 0 = positions
         b.slot_offset(8, flat)
         b.slot_scalar(6, "I", i, 0)
         b.slot_scalar(1, "I", dim, 0)

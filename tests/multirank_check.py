@@ -61,6 +61,25 @@ def main():
                 print("MISMATCH sharded vs single", (dtype, metric, n, d, k, nq))
             full.free()
         gs.free()
+    # external ids and a global row mask on a sharded space: ids table replicated, mask re-based per shard
+    n, d, k = 30000, 64, 10
+    gs = eng.synthetic(mv.DataType.UInt8, mv.DistanceMetric.L2, n, d, seed=77)
+    ext = (np.arange(n, dtype=np.uint64)[::-1] * 7 + 5).copy()
+    excluded = (np.arange(n) % 3) == 0
+    gs.set_ids(ext)
+    gs.set_row_mask(excluded)
+    q = mv.synth_fill_host(3, 78, 0, 20, d)
+    ids, sc, isc = gs.search(q, k)
+    if rank == 0:
+        db = mv.synth_fill_host(3, 77, 0, n, d)
+        keep = np.flatnonzero(~excluded)
+        for qi in range(20):
+            o_ids, _, o_isc = oracle.topk(db[keep], 3, 0, q[qi], k)
+            want = ext[keep[o_ids.astype(np.int64)]]
+            if ids[qi].tolist() != want.tolist() or isc[qi].tolist() != o_isc.tolist():
+                failures += 1
+                print("MISMATCH external ids / mask on shards, query", qi)
+    gs.free()
     dist.barrier()
     if rank == 0:
         print("multirank ok" if failures == 0 else "multirank FAILED", "world", world)

@@ -351,6 +351,70 @@ def test_upload_applies_the_files_tombstones(engine, tmp_path):
     assert ids[0].tolist() == o_ids.tolist() and ids[0][0] != 0
 
 
+def test_external_ids_are_reported_and_ties_still_break_by_position(engine):
+    # vector_ids_block_index (schema/core.fbs:54): results carry ids[row]; duplicated rows tie, the lower POSITION wins
+    base = mv.synth_fill_host(oracle.U8, 11, 0, 3000, 128)
+    db = np.concatenate([base, base])                              # every row twice: position p and p + 3000
+    ext = (np.arange(len(db), dtype=np.uint64)[::-1] * 3 + (1 << 33)).copy()   # decreasing, above 2^32
+    gs = engine.from_host(db, mv.DataType.UInt8, mv.DistanceMetric.L2)
+    q = mv.synth_fill_host(oracle.U8, 12, 0, 40, 128)
+    try:
+        for path in (1, 2):
+            engine.set_path(path)
+            gs.set_ids(ext)
+            ids, sc, isc = gs.search(q, 8)
+            gs.set_ids(None)
+            pos, _, isc0 = gs.search(q, 8)
+            for qi in range(len(q)):
+                o_ids, _, o_isc = oracle.topk(db, oracle.U8, oracle.L2, q[qi], 8)
+                assert pos[qi].tolist() == o_ids.tolist() and isc[qi].tolist() == o_isc.tolist()
+                assert ids[qi].tolist() == ext[o_ids.astype(np.int64)].tolist()
+        with pytest.raises(mv.DimensionMismatch):
+            gs.set_ids(ext[:10])
+    finally:
+        engine.set_path(0)
+        gs.free()
+
+
+def test_upload_applies_ids_and_tombstone_list_and_filters_add_to_them(engine, tmp_path):
+    n, d = 3000, 32
+    rows = mv.synth_fill_host(oracle.F32, 98, 0, n, d)
+    ext = np.arange(n, dtype=np.uint64) * 10 + 7
+    gone = np.arange(0, n, 5, dtype=np.uint64)                     # TombstoneInfo{SortedList}
+    year = (1990 + np.arange(n) % 40).astype(np.uint32)            # a metadata column to pre-filter on
+    b = mv.MvfBuilder()
+    b.add_vector_space("v", d, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors_raw("v", rows)
+    b.set_vector_ids("v", ext)
+    b.set_tombstone_list("v", gone)
+    b.add_metadata_column("year", mv.DataType.UInt32, year.tobytes())
+    path = str(tmp_path / "full.mvf")
+    b.save(path)
+    r = mv.MvfReader.open(path)
+    gs = engine.upload(r.vector_space("v"))
+    deleted = np.zeros(n, dtype=bool)
+    deleted[gone.astype(np.int64)] = True
+    raw, dt = r.metadata_column("year")
+    filt = mv.filter_range_bitmap(raw, dt, 2000, 2010)
+    assert np.array_equal(filt, ~((year >= 2000) & (year <= 2010)))
+    q = rows[0]                                                    # row 0 is deleted
+    ids, _, _ = gs.search(q, 6)
+    o_ids, _, _ = _masked_oracle(rows, oracle.F32, oracle.L2, q, 6, deleted)
+    assert ids[0].tolist() == ext[o_ids].tolist()
+    gs.set_row_mask(filt)                                          # filter AND tombstones
+    ids, _, _ = gs.search(q, 6)
+    o_ids, _, _ = _masked_oracle(rows, oracle.F32, oracle.L2, q, 6, deleted | filt)
+    assert ids[0].tolist() == ext[o_ids].tolist()
+    gs.set_row_mask(None)                                          # the filter goes, the deletions stay
+    ids, _, _ = gs.search(q, 6)
+    o_ids, _, _ = _masked_oracle(rows, oracle.F32, oracle.L2, q, 6, deleted)
+    assert ids[0].tolist() == ext[o_ids].tolist()
+    gs.set_tombstones(None)                                        # explicit un-delete: row 0 finds itself
+    ids, _, _ = gs.search(q, 1)
+    assert ids[0][0] == ext[0]
+    gs.free()
+
+
 def test_profile_counters(engine):
     gs = engine.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, 20000, 128, seed=1)
     engine.profile(True)

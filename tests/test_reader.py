@@ -293,3 +293,59 @@ def test_tombstone_bitmap_round_trip(tmp_path):
                         dict(name="plain", dimension=4, vector_type=0, distance_metric=0, data_type=0, data=rows[:3].tobytes())],
                        metadata_columns=[dict(name="ids", data_type=4, data=struct.pack("<40I", *range(40)))])
     assert py == data
+
+
+def test_vector_ids_tombstone_list_and_metadata_column_round_trip(tmp_path):
+    # the rest of what the schema reserves around the scan: external ids
+    # (vector_ids_block_index, schema/core.fbs:54; src/builder.rs:61,257-271), TombstoneInfo{SortedList}
+    # (schema/types.fbs:35-39) and metadata column bytes (schema/core.fbs:16-25).  The reference writes none of
+    # them (src/builder.rs:483-486) and reads back only column names (src/reader.rs:132-143).
+    rows = np.arange(30 * 4, dtype=np.float32).reshape(30, 4)
+    ids = (np.arange(30, dtype=np.uint64) * 1000003 + (1 << 40))
+    gone = np.array([2, 3, 17, 29], dtype=np.uint64)
+    price = np.linspace(0.0, 29.0, 30).astype(np.float32)
+    b = mv.MvfBuilder()
+    b.add_vector_space("a", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors("a", rows)
+    b.set_vector_ids("a", ids)
+    b.set_tombstone_list("a", gone)
+    b.add_vector_space("b", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors("b", rows[:5])
+    b.add_metadata_column("price", mv.DataType.Float32, price.tobytes())
+    with pytest.raises(mv.DimensionMismatch):
+        b.set_vector_ids("b", ids)                             # 30 ids for 5 rows
+    with pytest.raises(mv.Build):
+        b.set_tombstone_list("b", np.array([3, 3], dtype=np.uint64))   # not strictly ascending
+    path = str(tmp_path / "ids.mvf")
+    b.save(path)
+    r = mv.MvfReader.open(path)
+    r.validate_with_checksum()
+    a = r.vector_space("a")
+    assert np.array_equal(a.vector_ids(), ids) and r.vector_space("b").vector_ids() is None
+    assert np.array_equal(a.tombstone_list(), gone) and a.tombstones() is None
+    assert r.vector_space("b").tombstone_list() is None
+    raw, dt = r.metadata_column("price")
+    assert dt == mv.DataType.Float32 and np.array_equal(np.frombuffer(raw, dtype=np.float32), price)
+    with pytest.raises(mv.Build):
+        r.metadata_column("nope")
+    excl = mv.filter_range_bitmap(raw, dt, 10.0, 19.5)
+    assert np.array_equal(excl, ~((price >= 10.0) & (price <= 19.5)))
+    # independent Python writer: same bytes; independent parser: same indices
+    data = open(path, "rb").read()
+    py = fmt.build_mvf([dict(name="a", dimension=4, vector_type=0, distance_metric=0, data_type=0, data=rows.tobytes(),
+                             vector_ids=[int(x) for x in ids], tombstone_list=[int(x) for x in gone]),
+                        dict(name="b", dimension=4, vector_type=0, distance_metric=0, data_type=0, data=rows[:5].tobytes())],
+                       metadata_columns=[dict(name="price", data_type=0, data=price.tobytes())])
+    assert py == data
+    parsed = fmt.parse_mvf(data)
+    assert parsed["spaces"][0]["tombstones"] == dict(format=2, data_block_index=3, deleted_count=4)
+    assert parsed["spaces"][0]["vector_ids_block_index"] == 4 and parsed["spaces"][1]["vector_ids_block_index"] == 0
+
+
+@pytest.mark.parametrize("dt,np_dt", [(mv.DataType.UInt8, np.uint8), (mv.DataType.Int8, np.int8), (mv.DataType.UInt32, np.uint32),
+                                      (mv.DataType.UInt64, np.uint64), (mv.DataType.Float16, np.float16)])
+def test_filter_range_bitmap_every_dtype(dt, np_dt):
+    rng = np.random.default_rng(int(dt))
+    col = (rng.integers(-100, 100, 1003) if np_dt in (np.int8, np.float16) else rng.integers(0, 200, 1003)).astype(np_dt)
+    excl = mv.filter_range_bitmap(col, dt, 20, 90)
+    assert np.array_equal(excl, ~((col.astype(np.float64) >= 20) & (col.astype(np.float64) <= 90)))
