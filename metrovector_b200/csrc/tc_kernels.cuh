@@ -172,8 +172,11 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
 __device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
+// relaxed: the barrier only hands TMEM back (the tcgen05.ld results are already in registers after wait::ld), no
+// generic-memory data rides on it; the default release at cluster scope costs a MEMBAR.ALL.GPU per warp per tile,
+// which also waits for the candidate appends in flight (ncu: stall_membar 8 % of samples)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals may come from the peer CTA
     asm volatile(
