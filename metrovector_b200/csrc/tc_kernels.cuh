@@ -54,6 +54,7 @@ struct TcParams {
     uint32_t* gthr;                // [(mtiles rounded up to the cluster size)*BM] tightest k-th-best key any CTA has seen per query (atomicMin)
     uint64_t n;                    // resident rows
     uint32_t nq, k, cap;
+    uint32_t trigger;              // a buffer holding more than this many entries after a tile is compacted (<= cap - columns per thread)
     uint32_t kblocks;              // ceil(d * elem / 128)
     uint32_t mtiles, ntiles, chunks, tiles_per_chunk;
     int metric;                    // k::M_L2 / M_IP / M_COS
@@ -63,6 +64,7 @@ struct TcParams {
     uint32_t stages;               // depth of the operand ring (<= MAX_STAGES)
     uint32_t* progress;            // [items] database tiles each work item's producer has issued (pacing, see sync_window)
     uint32_t sync_window;          // 0 = off; else a producer stays within this many tiles of the slowest peer on its rows
+    unsigned long long* stats;     // -DMVF_TC_STATS builds only: cycle counters per role (see tc_path.cuh), else unused
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -250,6 +252,14 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
     return kth;
 }
 
+#ifdef MVF_TC_STATS
+#define TC_STAT_BEGIN(var) const long long var = clock64()
+#define TC_STAT_ADD(acc, var) acc += clock64() - var
+#else
+#define TC_STAT_BEGIN(var)
+#define TC_STAT_ADD(acc, var)
+#endif
+
 // MODE selects the ranking value computed from the accumulator `a` and the per-column parameter:
 //   MODE 0  (L2)            s = prm - 2a        prm = |x|^2           (float: fma; int: exact)
 //   MODE 1  (cosine / dot)  s = a * prm         prm = -1/|x| or -1    (float)   |  s = -a (int dot)
@@ -309,6 +319,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            [[maybe_unused]] long long st_total = 0, st_empty = 0, st_pace = 0;
+            TC_STAT_BEGIN(c_all);
             for (uint32_t w = w_first; w < items; w += w_step) {
                 const uint32_t mt = (w % mgroups) * CL + crank, ch = w / mgroups;
                 const uint32_t t0 = ch * p.tiles_per_chunk;
@@ -327,6 +339,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     if (pace && ((t - t0) & 3u) == 0) {
                         const uint32_t r = t - t0;
                         st_relaxed_gpu(p.progress + w, r);
+                        TC_STAT_BEGIN(c_p);
                         if (r > p.sync_window) {
                             for (int spin = 0; spin < 2048; spin++) {
                                 uint32_t slowest = 0xffffffffu;
@@ -335,9 +348,12 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                                 __nanosleep(512);
                             }
                         }
+                        TC_STAT_ADD(st_pace, c_p);
                     }
                     for (uint32_t kb = 0; kb < p.kblocks; kb++) {
+                        TC_STAT_BEGIN(c_e);
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);          // every CTA of the cluster released the slot
+                        TC_STAT_ADD(st_empty, c_e);
                         const uint32_t a_dst = smem_u32(ring + stage * SB);
                         const int kc = (int)(kb * (INT ? 128u : 64u));   // element coordinate along K
                         if (PAIR) {
@@ -362,22 +378,32 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 }
                 if (pace) st_relaxed_gpu(p.progress + w, 0xffffffffu);     // finished: never holds anyone back
             }
+#ifdef MVF_TC_STATS
+            TC_STAT_ADD(st_total, c_all);
+            if (p.stats) { atomicAdd(p.stats + 0, (unsigned long long)st_total); atomicAdd(p.stats + 1, (unsigned long long)st_empty); atomicAdd(p.stats + 2, (unsigned long long)st_pace); }
+#endif
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0 && (!PAIR || crank == 0)) {                       // pair form: the leader CTA issues for both
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            [[maybe_unused]] long long st_total = 0, st_full = 0, st_tempty = 0;
+            TC_STAT_BEGIN(c_all);
             for (uint32_t w = w_first; w < items; w += w_step) {
                 const uint32_t ch = w / mgroups;
                 const uint32_t t0 = ch * p.tiles_per_chunk;
                 const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
                 for (uint32_t t = t0; t < t1; t++) {
+                    TC_STAT_BEGIN(c_t);
                     if (PAIR) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
                     else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+                    TC_STAT_ADD(st_tempty, c_t);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     for (uint32_t kb = 0; kb < p.kblocks; kb++) {
+                        TC_STAT_BEGIN(c_f);
                         mbar_wait(full0 + 8 * stage, phase);           // TMA bytes have landed
+                        TC_STAT_ADD(st_full, c_f);
                         tcgen05_fence_after();
                         const uint32_t a_addr = smem_u32(ring + stage * SB);
                         const uint64_t adesc = make_sdesc(a_addr), bdesc = make_sdesc(a_addr + A_BYTES);
@@ -396,6 +422,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
+#ifdef MVF_TC_STATS
+            TC_STAT_ADD(st_total, c_all);
+            if (p.stats) { atomicAdd(p.stats + 3, (unsigned long long)st_total); atomicAdd(p.stats + 4, (unsigned long long)st_full); atomicAdd(p.stats + 5, (unsigned long long)st_tempty); }
+#endif
         }
     } else {
         // ===== epilogue: 2 warpgroups x 4 warps; a thread owns one query (TMEM lane) and the
@@ -412,18 +442,38 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         constexpr int CPLANE = EPI_COLS / 32;
         float* my_prm = prm + (size_t)(warp - 2) * 2 * EPI_COLS;
         uint32_t* my_valid = valid_s + (warp - 2) * 2 * CPLANE;
-        auto load_param = [&](uint32_t t, int j, bool* live) -> float {
+        // Split in two so the global loads of tile t+1 are ISSUED before tile t is processed and only CONSUMED after
+        // it (their ~1 us latency used to sit in front of every tile's accumulator wait): load_raw returns the
+        // untouched words, finish_param turns them into (parameter, live).
+        auto load_raw = [&](uint32_t t, int j, float* raw, uint32_t* mword) {
             const uint64_t row = (uint64_t)t * BN + grp * EPI_COLS + j * 32 + lane;
-            bool ok = row < p.n;
-            if (ok && p.mask != nullptr) ok = ((p.mask[row >> 5] >> (row & 31)) & 1u) == 0;
+            const bool in = row < p.n;
+            *mword = (in && p.mask != nullptr) ? p.mask[row >> 5] : 0u;
+            float v = 0.f;
+            if (in) {
+                if (MODE == 0) v = p.sq[row];                             // |x|^2 (int32 bits for integer spaces)
+                else if (!INT && p.metric == k::M_COS) v = p.norm[row];
+            }
+            *raw = v;
+        };
+        auto finish_param = [&](uint32_t t, int j, float raw, uint32_t mword, bool* live) -> float {
+            const uint64_t row = (uint64_t)t * BN + grp * EPI_COLS + j * 32 + lane;
+            const bool ok = row < p.n && ((mword >> (row & 31)) & 1u) == 0;
             *live = ok;
             if (!ok) return __int_as_float(0);
-            if (MODE == 0) return p.sq[row];                              // |x|^2 (int32 bits for integer spaces)
+            if (MODE == 0) return raw;
             if (INT) return __int_as_float(0);
-            if (p.metric == k::M_COS) { const float nm = p.norm[row]; return nm > 0.f ? -1.0f / nm : 0.0f; }
+            if (p.metric == k::M_COS) return raw > 0.f ? -1.0f / raw : 0.0f;
             return -1.0f;
         };
+        auto load_param = [&](uint32_t t, int j, bool* live) -> float {
+            float raw; uint32_t mw;
+            load_raw(t, j, &raw, &mw);
+            return finish_param(t, j, raw, mw, live);
+        };
         uint32_t acc = 0, acc_phase = 0;
+        [[maybe_unused]] long long st_total = 0, st_tfull = 0, st_compact = 0, st_tail = 0;
+        TC_STAT_BEGIN(c_all);
         for (uint32_t w = w_first; w < items; w += w_step) {
             const uint32_t mt = (w % mgroups) * CL + crank, ch = w / mgroups;
             const uint32_t t0 = ch * p.tiles_per_chunk;
@@ -468,19 +518,21 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             }
             for (uint32_t t = t0; t < t1; t++) {
                 const float* pr = my_prm + acc * EPI_COLS;
-                float nx[CPLANE];
-                unsigned nvw[CPLANE];
+                float nraw[CPLANE];
+                uint32_t nmw[CPLANE];
 #pragma unroll
-                for (int j = 0; j < CPLANE; j++) { nx[j] = 0.f; nvw[j] = 0; }
+                for (int j = 0; j < CPLANE; j++) { nraw[j] = 0.f; nmw[j] = 0; }
                 if (t + 1 < t1) {
 #pragma unroll
-                    for (int j = 0; j < CPLANE; j++) { bool lv; nx[j] = load_param(t + 1, j, &lv); nvw[j] = __ballot_sync(0xffffffffu, lv); }
+                    for (int j = 0; j < CPLANE; j++) load_raw(t + 1, j, &nraw[j], &nmw[j]);
                 }
                 const uint32_t* vs = my_valid + acc * CPLANE;
                 // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen.
                 // The word is read from L2 now and applied after this tile, so its latency is hidden.
                 const uint32_t gk = __ldcg(p.gthr + q);
+                TC_STAT_BEGIN(c_w);
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
+                TC_STAT_ADD(st_tfull, c_w);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * EPI_COLS;
                 for (int c2 = 0; c2 < EPI_COLS / (32 * LDG); c2++) {
@@ -548,8 +600,20 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             }
                         }
                     }
-                    // a buffer that could overflow during the next 32 columns is compacted now, by the whole warp
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > (int)p.cap - 32);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {                                         // all epilogue warps -> accumulator free
+                    if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * acc, 0));
+                    else mbar_arrive(tempty0 + 8 * acc);
+                }
+                // A buffer past its trigger level is compacted now, by the whole warp -- after the accumulator went back to
+                // the issuer, so the sort overlaps the next tiles' MMAs instead of holding up every other warp's tile.
+                // trigger <= cap - EPI_COLS: whatever the next tile appends still fits.
+                {
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > (int)p.trigger);
+                    TC_STAT_BEGIN(c_c);
                     while (need) {
                         const int owner = __ffs(need) - 1;
                         need &= need - 1;
@@ -569,13 +633,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             }
                         }
                     }
-                    }
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) {                                         // all epilogue warps -> accumulator free
-                    if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * acc, 0));
-                    else mbar_arrive(tempty0 + 8 * acc);
+                    TC_STAT_ADD(st_compact, c_c);
                 }
                 if (gk < thr_key) { thr_key = gk; refresh_threshold(); }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -583,13 +641,16 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     float* prn = my_prm + acc * EPI_COLS;
 #pragma unroll
                     for (int j = 0; j < CPLANE; j++) {
-                        prn[j * 32 + lane] = nx[j];
-                        if (lane == 0) my_valid[acc * CPLANE + j] = nvw[j];
+                        bool lv;
+                        prn[j * 32 + lane] = finish_param(t + 1, j, nraw[j], nmw[j], &lv);
+                        const unsigned vw = __ballot_sync(0xffffffffu, lv);
+                        if (lane == 0) my_valid[acc * CPLANE + j] = vw;
                     }
                 }
                 __syncwarp();
             }
             // end of the work item: every query's buffer becomes a sorted list of its k best
+            TC_STAT_BEGIN(c_tail);
             for (int owner = 0; owner < 32; owner++) {
                 const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
                 u64* obuf = cta_cand + (size_t)(quarter * 32 + owner) * p.cap;
@@ -604,7 +665,15 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 }
                 __syncwarp();
             }
+            TC_STAT_ADD(st_tail, c_tail);
         }
+#ifdef MVF_TC_STATS
+        TC_STAT_ADD(st_total, c_all);
+        if (p.stats && lane == 0 && warp == 2) {
+            atomicAdd(p.stats + 6, (unsigned long long)st_total); atomicAdd(p.stats + 7, (unsigned long long)st_tfull);
+            atomicAdd(p.stats + 8, (unsigned long long)st_compact); atomicAdd(p.stats + 9, (unsigned long long)st_tail);
+        }
+#endif
     }
     tcgen05_fence_before();
     __syncthreads();

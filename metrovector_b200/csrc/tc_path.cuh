@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -91,10 +92,21 @@ inline int stages_for(uint32_t cap, int eg, bool pair) {
     while (s > 2 && smem_bytes(cap, eg, s, pair) > 227 * 1024) s--;
     return s;
 }
-inline uint32_t cap_for_k(uint32_t k) {
-    static const int big = std::getenv("MVF_TC_BIGCAP") ? std::atoi(std::getenv("MVF_TC_BIGCAP")) : 0;
-    if (big) return k <= 16 ? 128u : k <= 64 ? 256u : 512u;
-    return k <= 16 ? 128u : k <= 112 ? 256u : 512u;   // cap >= k + 32 (one 32-column group) + headroom
+// Candidate buffers.  A buffer is compacted (bitonic sort of the next power of two >= its fill, keep k) between
+// tiles once it holds more than `trigger` entries.  Sort cost per append ~ P log^2 P / (P - k) favours SMALL sorts
+// for small k (k = 10: P = 64) and P ~ 2.5k for large k, so the trigger sits just under a power of two >= 2k + 16;
+// the buffer itself (cap, power of two, <= MAX_CAP) also has to take one more tile of appends past the trigger
+// (BN / eg columns per thread).
+inline uint32_t trigger_for_k(uint32_t k) {
+    uint32_t p2 = 32;
+    while (p2 < 2 * k + 16) p2 <<= 1;
+    return p2 - 16;
+}
+inline uint32_t cap_for_k(uint32_t k, int eg) {
+    const uint32_t want = trigger_for_k(k) + (uint32_t)(BN / eg);
+    uint32_t cap = 128;
+    while (cap < want && cap < (uint32_t)MAX_CAP) cap <<= 1;
+    return cap;
 }
 
 // K2 takes f16 spaces with f16 queries and int8/uint8 spaces (any metric except integer cosine,
@@ -155,13 +167,13 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     const uint32_t mgroups = (mtiles + CL - 1) / CL;
     const uint32_t items = mgroups * chunks;
     const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count / CL, items) * CL;
-    const uint32_t cap = cap_for_k(a.k);
     const uint32_t kblocks = (a.d * es + BKB - 1) / BKB;
     int EG = st.epi_groups ? st.epi_groups : (kblocks <= 2 ? 4 : 2);
+    uint32_t cap = cap_for_k(a.k, EG);
     // short rows are bound by the epilogue, and a pair's leader waits for the slower of two epilogues (measured on
     // config E batched: 840 -> 620 TOP/s), so the pair form is for rows of more than two K blocks (MVF_TC_PAIR=2 forces it)
     const bool pair = CL == 2 && (st.pair == 2 || (st.pair == 1 && kblocks > 2));
-    if (smem_bytes(cap, EG, 3, pair) > 227 * 1024) EG = 2;
+    if (EG == 4 && smem_bytes(cap, EG, 3, pair) > 227 * 1024) { EG = 2; cap = cap_for_k(a.k, EG); }
     const int stages = stages_for(cap, EG, pair);
 
     st.qprep.reserve((size_t)mtiles * BM * qpitch);
@@ -196,6 +208,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
+    p.trigger = std::min<uint32_t>(trigger_for_k(a.k), cap - (uint32_t)(BN / EG));
     p.kblocks = kblocks;
     p.mtiles = mtiles; p.ntiles = ntiles; p.chunks = chunks; p.tiles_per_chunk = tiles_per_chunk;
     p.metric = a.metric; p.is_int = is_int ? 1 : 0;
@@ -204,6 +217,13 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     p.l2_prefetch_tiles = (uint32_t)st.l2_prefetch;
     p.stages = (uint32_t)stages;
     p.progress = (uint32_t*)st.progress.p; p.sync_window = sync_window;
+    p.stats = nullptr;
+#ifdef MVF_TC_STATS
+    static Buf stats_buf;
+    stats_buf.reserve(16 * 8);
+    TC_CUDA_CHECK(cudaMemsetAsync(stats_buf.p, 0, 16 * 8, stream));
+    p.stats = (unsigned long long*)stats_buf.p;
+#endif
     // the pair form's instruction spans both CTAs: M = 256
     p.idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
     if (a.dump) {
@@ -224,6 +244,17 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     TC_CUDA_CHECK(cudaLaunchKernelExC(&cfg, fn, args));
     TC_CUDA_CHECK(cudaGetLastError());
     launches++;
+#ifdef MVF_TC_STATS
+    {   // diagnostic build: where each role's cycles went (sums over CTAs; one producer, one issuer, one epilogue warp each)
+        unsigned long long h[16];
+        TC_CUDA_CHECK(cudaStreamSynchronize(stream));
+        TC_CUDA_CHECK(cudaMemcpy(h, stats_buf.p, sizeof(h), cudaMemcpyDeviceToHost));
+        auto pct = [&](int part, int whole) { return h[whole] ? 100.0 * (double)h[part] / (double)h[whole] : 0.0; };
+        std::fprintf(stderr, "[tc stats] producer: wait-empty %.1f%% pacing %.1f%% | issuer: wait-full %.1f%% wait-accumulator %.1f%% | "
+                             "epilogue warp: wait-accumulator-ready %.1f%% compaction %.1f%% item-tail %.1f%%\n",
+                     pct(1, 0), pct(2, 0), pct(4, 3), pct(5, 3), pct(7, 6), pct(8, 6), pct(9, 6));
+    }
+#endif
     SearchResult r;
     r.lists = (const u64*)st.lists.p; r.chunks = chunks * EG; r.qconst = (const float*)st.qconst.p;
     r.dump = (const float*)st.dump.p; r.dump_cols = ntiles * BN; r.launches = launches;
