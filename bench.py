@@ -56,6 +56,10 @@ DB_SEED, Q_SEED = 0x4D564631, 0x4D564632
 # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_ncu_{B,D,E}.md), as bytes per algorithmic
 # byte: B 3.0761e9 / 3.072e9, D 154.0147e9 / 153.6e9 (the extra 0.27% are the row norms), E 25.6043e9 / 25.6e9
 NCU_TRAFFIC_RATIO = {"B": 3.076061e9 / 3.072e9, "D": 154.014740e9 / 153.6e9, "E": 25.604293e9 / 25.6e9}
+# same for the tensor kernel (profiles/r1_ncu_{C,D1024,E1024}.md): C 10M rows, D1024 on a 20M-row slab, E1024 on a
+# 100M-row slab; the excess over the rows is mostly rows fetched again by query-tile groups in other scheduling rounds
+NCU_TRAFFIC_RATIO_TC = {"C": (19.167781e9 + 1.196128e9) / 15.36e9, "D1024": (52.810941e9 + 0.141213e9) / 30.72e9,
+                        "E1024": (13.728670e9 + 0.195724e9) / 12.8e9}
 
 
 def describe(wl, n, d, dt, metric, k, batch):
@@ -322,7 +326,7 @@ def main():
         bytes_per_launch = gs.local_n * d * es * (1 if prof["last_path"] == 2 else 1)
         launches_per_step = prof["scan_launches"] / max(1, args.steps)
         achieved = bytes_per_launch / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-        ratio = NCU_TRAFFIC_RATIO.get(args.workload) if prof["last_path"] == 1 else None
+        ratio = (NCU_TRAFFIC_RATIO if prof["last_path"] == 1 else NCU_TRAFFIC_RATIO_TC).get(args.workload)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (bytes_per_launch * ratio) if ratio else None,
                 "traffic_source": ("ncu --set full of this workload, profiles/r1_ncu_%s.md, scaled by rows" % args.workload) if ratio else None,
@@ -334,11 +338,13 @@ def main():
             tf = flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0
             try:
                 with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                    tpeak = float(json.load(fh)["bf16_tflops"])
+                    pk = json.load(fh)
+                tpeak, tsust = float(pk["bf16_tflops"]), float(pk.get("bf16_tflops_sustained", 0.0)) or None
             except Exception:
-                tpeak = 1590.0
+                tpeak, tsust = 1590.0, None
             roof.update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                         "algorithmic_flops_per_launch": flops})
+                         "algorithmic_flops_per_launch": flops, "peak_sustained": tsust,
+                         "frac_of_sustained": (tf / tsust) if tsust else None})
         line = {
             "metric": "brute-force top-k QPS", "value": args.steps * batch / (dev_ms * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,

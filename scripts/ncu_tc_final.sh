@@ -15,4 +15,4 @@ $D > gpurun_out/plain_D1024.log 2>&1 && ncu --set full --clock-control none --im
 E1="python bench.py --workload E1024 --rows 100000000 --steps 2 --warmup 3 --no-cpu"
 $E1 > gpurun_out/plain_E1024.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_topk_tc -s 3 -c 1 -o /tmp/prof_E1024 $E1 > gpurun_out/ncu_E1024.log 2>&1; exp E1024
 ls -la gpurun_out | grep prof_
-tail -2 gpurun_out/ncu_C.log gpurun_out/ncu_D1024.log gpurun_out/ncu_E1024.log
+for f in C D1024 E1024; do tail -n 2 gpurun_out/ncu_$f.log; done
