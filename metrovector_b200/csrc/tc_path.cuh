@@ -45,7 +45,7 @@ struct TcState {
     int l2_prefetch = 0;           // (measured slower: the kernel is power-capped, extra L2 traffic costs clocks) database tiles prefetched into L2 ahead of the TMA loads (MVF_TC_PREFETCH=0..4)
     int epi_groups = 0;            // 0 = by row length (4 epilogue warpgroups for K <= 256 bytes, else 2); MVF_TC_EPI_GROUPS=2|4
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
-    int sync_window = -1;          // pacing of work items that share database tiles: -1 = auto (8 tiles whenever two or more query-tile groups share rows), 0 = off, else tiles (MVF_TC_SYNC_WINDOW)
+    int sync_window = -1;          // pacing of work items that share database tiles: -1 = auto (about 16 MB of tiles in flight, whenever two or more query-tile groups share rows), 0 = off, else tiles (MVF_TC_SYNC_WINDOW)
     int pair = 1;                  // clusters of two run cta_group::2 MMAs (256 queries x 256 rows, half the database tile per CTA) instead of multicasting whole tiles (MVF_TC_PAIR=0|1)
     // auto path: batches at least this large go to the tensor cores.  Measured crossover (scripts/crossover.py):
     // f16 768-d rows: the scan kernel pays a convert + FMA per element per query and loses from 4 queries on;
@@ -182,7 +182,16 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     st.lists.reserve((size_t)a.nq * chunks * EG * a.k * 8);
     st.gthr.reserve((size_t)mgroups * CL * BM * 4);
     TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mgroups * CL * BM * 4, stream));
-    const uint32_t sync_window = st.sync_window >= 0 ? (uint32_t)st.sync_window : (mgroups >= 2 ? 8u : 0u);
+    // pacing window (tiles a producer may lead the slowest item on the same rows): sized so that the tiles "in
+    // flight" across all concurrently processed runs stay around 16 MB of L2 -- 8 tiles of 393 KB for config C
+    // (4.6 runs at a time), 2 for D batch 1024 (18.5 runs; measured 1 105 vs 1 075 TFLOP/s at 8), dozens for 32 KB tiles
+    uint32_t sync_window = 0;
+    if (st.sync_window >= 0) sync_window = (uint32_t)st.sync_window;
+    else if (mgroups >= 2) {
+        const double runs = std::max(1.0, (double)(grid / CL) / (double)mgroups);
+        const double tile_bytes = (double)BN * (double)a.pitch;
+        sync_window = (uint32_t)std::min(64.0, std::max(2.0, 16.0 * 1048576.0 / (runs * tile_bytes)));
+    }
     if (sync_window) {
         st.progress.reserve((size_t)items * 4);
         TC_CUDA_CHECK(cudaMemsetAsync(st.progress.p, 0, (size_t)items * 4, stream));
