@@ -4,18 +4,21 @@
 // Shape of the work: S = Q (nq x d) . X^T (n x d), both operands K-major exactly as stored
 // (row-major queries, row-major resident rows), so no transposes.  One CTA tile = 128 queries x
 // 256 database rows; K is walked in 128-byte blocks (64 f16 / 128 int8).  Operands are staged by
-// TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 4-stage shared-memory ring, multiplied by
-// single-thread tcgen05.mma instructions (kind::f16 with f32 accumulation, kind::i8 with s32
-// accumulation) into TMEM, and the two 128x256 accumulators in TMEM are double buffered so the
-// epilogue of tile i overlaps the MMAs of tile i+1.  The distance matrix never leaves TMEM /
-// registers: each epilogue thread owns one query (one TMEM lane), reads its 256 scores with
-// tcgen05.ld, turns them into the metric's ranking value and keeps only values that beat the
-// query's current k-th best (threshold in a register, rare appends to a per-query buffer, warp-
-// cooperative bitonic compaction when a buffer fills).
+// TMA (cp.async.bulk.tensor, 128-byte swizzle) into a shared-memory ring (3-4 stages of 48 KiB, or
+// 5-6 of 32 KiB in the CTA-pair form), multiplied by single-thread tcgen05.mma instructions
+// (kind::f16 with f32 accumulation, kind::i8 with s32 accumulation; cta_group::2 spanning a
+// cluster of two CTAs for long rows) into TMEM, and the two 128x256 accumulators in TMEM are
+// double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.  The distance matrix
+// never leaves TMEM / registers: each epilogue thread owns one query (one TMEM lane), reads its
+// 256 scores with tcgen05.ld, turns them into the metric's ranking value and keeps only values
+// that beat the query's current k-th best (threshold in a register, a 3-input min tree per 32
+// columns as the common-case test, rare appends to a per-query buffer, warp-cooperative bitonic
+// compaction between tiles once a buffer passes its trigger level).
 //
-// Warp roles (64 + 128*EG threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then EG
-// epilogue warpgroups (TMEM lane quarter = warp_id % 4, column slice = group), each warp decoupled from the
-// others (no CTA-wide barrier in the steady state).
+// Warp roles (64 + 128*EG threads): warp 0 = TMA producer (also paces itself against the other
+// clusters working on the same database tiles, so those stay in L2), warp 1 = TMEM allocator +
+// MMA issuer, then EG epilogue warpgroups (TMEM lane quarter = warp_id % 4, column slice = group),
+// each warp decoupled from the others (no CTA-wide barrier in the steady state).
 // Replaces the same reference loop as K1 (examples/similarity_search.rs:147-169) for large batches.
 #pragma once
 #include <cuda.h>

@@ -46,6 +46,7 @@ struct TcState {
     int epi_groups = 0;            // 0 = by row length (4 epilogue warpgroups for K <= 256 bytes, else 2); MVF_TC_EPI_GROUPS=2|4
     int cluster = 2;               // CTAs per cluster sharing database tiles by TMA multicast (MVF_TC_CLUSTER=1|2)
     int sync_window = -1;          // pacing of work items that share database tiles: -1 = auto (about 16 MB of tiles in flight, whenever two or more query-tile groups share rows), 0 = off, else tiles (MVF_TC_SYNC_WINDOW)
+    int items_per_sm = 8;          // work items per SM the database is cut into (MVF_TC_ITEMS_PER_SM)
     int pair = 1;                  // clusters of two run cta_group::2 MMAs (256 queries x 256 rows, half the database tile per CTA) instead of multicasting whole tiles (MVF_TC_PAIR=0|1)
     // auto path: batches at least this large go to the tensor cores.  Measured crossover (scripts/crossover.py):
     // f16 768-d rows: the scan kernel pays a convert + FMA per element per query and loses from 4 queries on;
@@ -73,6 +74,7 @@ inline void init(TcState& st) {
     st.encode = (EncodeTiledFn)fn;
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch_f16 = st.min_batch_i8 = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
+    if (const char* c = std::getenv("MVF_TC_ITEMS_PER_SM")) st.items_per_sm = std::max(1, std::min(64, std::atoi(c)));
     if (const char* c = std::getenv("MVF_TC_PAIR")) st.pair = std::max(0, std::min(2, std::atoi(c)));
     if (const char* c = std::getenv("MVF_TC_SYNC_WINDOW")) st.sync_window = std::max(-1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_EPI_GROUPS")) st.epi_groups = std::atoi(c) == 4 ? 4 : (std::atoi(c) == 2 ? 2 : 0);
@@ -159,7 +161,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     const uint32_t ntiles = (uint32_t)((a.n + BN - 1) / BN);
     // work items = (query tile, contiguous run of database tiles); ~8 items per SM, each item keeps
     // its own running thresholds, the item lists are merged afterwards
-    uint32_t chunks = std::max<uint32_t>(1, (8u * (uint32_t)sm_count + mtiles - 1) / mtiles);
+    uint32_t chunks = std::max<uint32_t>(1, ((uint32_t)st.items_per_sm * (uint32_t)sm_count + mtiles - 1) / mtiles);
     chunks = std::min(chunks, ntiles);
     const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
     chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
