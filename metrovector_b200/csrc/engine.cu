@@ -107,7 +107,11 @@ struct mvf_gpu {
     int upload_threads = 8;                // MVF_UPLOAD_THREADS
     std::map<std::pair<const void*, size_t>, int> occ_cache;
     mvf::tc::TcState tc;
+    // one stream + one set of scratch buffers per engine: every entry point that touches them takes this lock, so
+    // calls from several host threads are serialised instead of racing (SURVEY.md 8b "Threading")
+    std::recursive_mutex mu;
 };
+using EngineLock = std::lock_guard<std::recursive_mutex>;
 
 struct mvf_gpu_space {
     mvf_gpu* g = nullptr;
@@ -644,7 +648,7 @@ void mvf_gpu_shutdown(mvf_gpu* g) {
 }
 
 int mvf_gpu_set_stream(mvf_gpu* g, void* cuda_stream) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         CUDA_CHECK(cudaSetDevice(g->device));
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
         if (g->own_stream) { cudaStreamDestroy(g->stream); g->own_stream = false; }
@@ -675,7 +679,7 @@ int mvf_gpu_comm_unique_id(void* out_128_bytes) {
 }
 
 int mvf_gpu_comm_init(mvf_gpu* g, const void* unique_id_128_bytes, int rank, int world) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         if (world < 1 || rank < 0 || rank >= world) throw MvfError::nccl("invalid rank/world");
         CUDA_CHECK(cudaSetDevice(g->device));
         g->rank = rank; g->world = world;
@@ -686,7 +690,7 @@ int mvf_gpu_comm_init(mvf_gpu* g, const void* unique_id_128_bytes, int rank, int
 }
 
 int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* sp, mvf_gpu_space** out) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         *out = nullptr;
         const VectorSpace& vs = sp->vs;
         if (vs.vector_type() != VectorType::Dense)
@@ -731,7 +735,7 @@ int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* sp, mvf_gpu_space** out) {
 
 int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type, int metric, uint64_t local_n, uint32_t dimension,
                             uint64_t row_base, uint64_t global_n, mvf_gpu_space** out) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         *out = nullptr;
         if (row_base + local_n > global_n) throw MvfError::index_out_of_bounds(row_base + local_n, global_n);
         mvf_gpu_space* s = alloc_space(g, data_type, metric, local_n, dimension, row_base, global_n);
@@ -746,7 +750,7 @@ int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type, int met
 
 int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t global_n, uint32_t dimension, uint64_t seed,
                             mvf_gpu_space** out) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         *out = nullptr;
         uint64_t begin = 0, count = global_n;
         shard_range(global_n, g->world, g->rank, &begin, &count);
@@ -771,16 +775,20 @@ int mvf_gpu_space_synthetic(mvf_gpu* g, int data_type, int metric, uint64_t glob
     });
 }
 
-void mvf_gpu_space_free(mvf_gpu_space* s) { free_space(s); }
+void mvf_gpu_space_free(mvf_gpu_space* s) {
+    if (!s) return;
+    EngineLock engine_lock(s->g->mu);
+    free_space(s);
+}
 
 int mvf_gpu_space_set_tombstones(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
-    return guard([&] { set_mask_part(s, 0, bitmap, nbits); });
+    return guard([&] { EngineLock engine_lock(s->g->mu); set_mask_part(s, 0, bitmap, nbits); });
 }
 int mvf_gpu_space_set_ids(mvf_gpu_space* s, const uint64_t* ids, uint64_t count) {
-    return guard([&] { set_ids(s, ids, count); });
+    return guard([&] { EngineLock engine_lock(s->g->mu); set_ids(s, ids, count); });
 }
 int mvf_gpu_space_set_row_mask(mvf_gpu_space* s, const uint8_t* bitmap, uint64_t nbits) {
-    return guard([&] { set_row_mask(s, bitmap, nbits); });
+    return guard([&] { EngineLock engine_lock(s->g->mu); set_row_mask(s, bitmap, nbits); });
 }
 
 int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base, uint64_t* global_n,
@@ -806,7 +814,7 @@ int mvf_gpu_space_upload_stats(const mvf_gpu_space* s, int* path, double* second
 const char* mvf_gpu_space_upload_note(const mvf_gpu_space* s) { return s ? s->upload_note.c_str() : ""; }
 
 int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         if (local_start + count > s->local_n) throw MvfError::index_out_of_bounds(local_start + count, s->local_n);
         if (!count) return;
         CUDA_CHECK(cudaSetDevice(s->g->device));
@@ -817,7 +825,7 @@ int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64
 }
 
 int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out_sq) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         CUDA_CHECK(cudaSetDevice(s->g->device));
         CUDA_CHECK(cudaStreamSynchronize(s->g->stream));
         if (out_norm) CUDA_CHECK(cudaMemcpy(out_norm, s->norm, s->local_n * 4, cudaMemcpyDeviceToHost));
@@ -828,7 +836,7 @@ int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, float* out
 // CRC-32 of the resident rows, computed on the device (rows must be resident without padding, i.e. row
 // bytes a multiple of 16, and the space must not be sharded)
 int mvf_gpu_space_checksum(mvf_gpu_space* s, uint32_t* out_crc, double* out_ms) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         mvf_gpu* g = s->g;
         const size_t rowbytes = (size_t)s->d * element_size((DataType)s->dtype);
         if (rowbytes != s->pitch) throw MvfError::build_error("device checksum needs rows of a multiple of 16 bytes");
@@ -883,7 +891,7 @@ int mvf_gpu_space_checksum(mvf_gpu_space* s, uint32_t* out_crc, double* out_ms) 
 
 // integrity on upload: device CRC of the resident block against the manifest entry of the file
 int mvf_gpu_space_verify_checksum(mvf_gpu_space* s, const mvf_space* sp) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         const VectorSpace& vs = sp->vs;
         const auto& blocks = vs.reader()->blocks();
         const SpaceInfo* info = nullptr;
@@ -902,7 +910,7 @@ int mvf_gpu_space_verify_checksum(mvf_gpu_space* s, const mvf_space* sp) {
 }
 
 int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uint32_t count, int as_f32, void* out) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         mvf_gpu* g = s->g;
         if (!count) return;
         if (!ids || !out) throw MvfError::build_error("null argument");
@@ -933,12 +941,12 @@ int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uint32_t co
 
 int mvf_gpu_search_device(mvf_gpu_space* s, const void* d_queries, int query_dtype, uint32_t nq, uint32_t k, int metric,
                           uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_iscores) {
-    return guard([&] { search_device(s, d_queries, query_dtype, nq, k, metric, d_out_ids, d_out_scores, d_out_iscores); });
+    return guard([&] { EngineLock engine_lock(s->g->mu); search_device(s, d_queries, query_dtype, nq, k, metric, d_out_ids, d_out_scores, d_out_iscores); });
 }
 
 int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq, uint32_t k, int metric,
                    uint64_t* out_ids, float* out_scores, int32_t* out_iscores) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         mvf_gpu* g = s->g;
         if (!queries || !out_ids) throw MvfError::build_error("null argument");
         if (nq == 0) throw MvfError::build_error("search needs at least one query");
@@ -982,7 +990,7 @@ int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint3
 
 int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq, uint32_t k, int metric,
                     float* out, uint64_t out_elems, uint32_t* out_rows, uint32_t* out_cols) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(s->g->mu);
         mvf_gpu* g = s->g;
         if (metric == MVF_METRIC_SPACE_DEFAULT) metric = s->metric;
         if (!mvf::tc::eligible(g->tc, 2, s->dtype, query_dtype, metric, nq, k, s->local_n, s->d, s->pitch))
@@ -1005,14 +1013,14 @@ int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint
 }
 
 int mvf_gpu_set_path(mvf_gpu* g, int path) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         if (path < 0 || path > 2) throw MvfError::build_error("path must be 0 (auto), 1 (scan) or 2 (tensor)");
         g->path = path;
     });
 }
 
 int mvf_gpu_profile(mvf_gpu* g, int enable) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         CUDA_CHECK(cudaSetDevice(g->device));
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
         flush_profile(g);
@@ -1022,7 +1030,7 @@ int mvf_gpu_profile(mvf_gpu* g, int enable) {
 }
 
 int mvf_gpu_profile_read(mvf_gpu* g, double* scan_ms_total, uint64_t* scan_launches, uint64_t* all_launches, int* last_path) {
-    return guard([&] {
+    return guard([&] { EngineLock engine_lock(g->mu);
         CUDA_CHECK(cudaSetDevice(g->device));
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
         flush_profile(g);
@@ -1034,7 +1042,7 @@ int mvf_gpu_profile_read(mvf_gpu* g, double* scan_ms_total, uint64_t* scan_launc
 }
 
 int mvf_gpu_synchronize(mvf_gpu* g) {
-    return guard([&] { CUDA_CHECK(cudaSetDevice(g->device)); CUDA_CHECK(cudaStreamSynchronize(g->stream)); });
+    return guard([&] { EngineLock engine_lock(g->mu); CUDA_CHECK(cudaSetDevice(g->device)); CUDA_CHECK(cudaStreamSynchronize(g->stream)); });
 }
 
 }  // extern "C"

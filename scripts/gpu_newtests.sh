@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "external_ids or tombstone or row_mask" 2>&1 | tail -15
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "threads or external_ids or profile" 2>&1 | tail -6
+timeout 200 python scripts/bench_summary.py A B --steps 30 --warmup 5

@@ -415,6 +415,35 @@ def test_upload_applies_ids_and_tombstone_list_and_filters_add_to_them(engine, t
     gs.free()
 
 
+def test_searches_from_several_host_threads_are_serialised_not_raced(engine):
+    # one engine = one stream + one set of scratch buffers; the library locks per engine (SURVEY.md 8b "Threading"),
+    # so concurrent callers (ctypes drops the GIL during the call) must all get the serial answers
+    import threading
+    gs = engine.synthetic(mv.DataType.UInt8, mv.DistanceMetric.L2, 300000, 128, seed=5)
+    q = mv.synth_fill_host(oracle.U8, 6, 0, 48, 128)
+    serial = [gs.search(q[i], 10) for i in range(len(q))]
+    batch = gs.search(q[:16], 10)                                  # a tensor-path batch in the mix
+    got, errs = [None] * len(q), []
+
+    def work(t):
+        try:
+            for i in range(t, len(q), 4):
+                got[i] = gs.search(q[i], 10)
+                if i % 8 == 0:
+                    b = gs.search(q[:16], 10)
+                    assert np.array_equal(b[0], batch[0]) and np.array_equal(b[2], batch[2])
+        except Exception as e:                                     # surfaced below, not swallowed
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for i in range(len(q)):
+        assert np.array_equal(got[i][0], serial[i][0]) and np.array_equal(got[i][2], serial[i][2]), i
+    gs.free()
+
+
 def test_profile_counters(engine):
     gs = engine.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, 20000, 128, seed=1)
     engine.profile(True)
