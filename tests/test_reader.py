@@ -349,3 +349,44 @@ def test_filter_range_bitmap_every_dtype(dt, np_dt):
     col = (rng.integers(-100, 100, 1003) if np_dt in (np.int8, np.float16) else rng.integers(0, 200, 1003)).astype(np_dt)
     excl = mv.filter_range_bitmap(col, dt, 20, 90)
     assert np.array_equal(excl, ~((col.astype(np.float64) >= 20) & (col.astype(np.float64) <= 90)))
+
+
+def test_footer_corruption_never_crashes_the_auxiliary_accessors(tmp_path):
+    # the same single-byte sweep as test_invalid_footer_length..., over a footer that names an ids block, a
+    # tombstone list and a metadata column: every accessor either answers or raises an MvfError
+    rows = np.arange(12 * 4, dtype=np.float32).reshape(12, 4)
+    good = fmt.build_mvf([dict(name="a", dimension=4, vector_type=0, distance_metric=0, data_type=0, data=rows.tobytes(),
+                               vector_ids=list(range(100, 112)), tombstone_list=[1, 5]),
+                          dict(name="b", dimension=4, vector_type=0, distance_metric=2, data_type=0, data=rows[:3].tobytes(),
+                               tombstones=b"\x05")],
+                         metadata_columns=[dict(name="price", data_type=0, data=rows[:, 0].tobytes())])
+    flen = struct.unpack_from("<I", good, len(good) - 8)[0]
+    start = len(good) - 8 - flen
+    path = str(tmp_path / "flip.mvf")
+    opened = 0
+    for i in range(start, len(good) - 8):
+        for mask in (0xFF, 0x01, 0x80):
+            bad = bytearray(good)
+            bad[i] ^= mask
+            open(path, "wb").write(bytes(bad))
+            try:
+                r = mv.MvfReader.open(path)
+            except mv.MvfError:
+                continue
+            opened += 1
+            for call in (r.validate, r.validate_with_checksum, lambda: r.metadata_column("price")):
+                try:
+                    call()
+                except mv.MvfError:
+                    pass
+            for nm in r.vector_space_names():
+                try:
+                    s = r.vector_space(nm)
+                except mv.MvfError:
+                    continue
+                for call in (s.vector_ids, s.tombstone_list, s.tombstones, s.scannable_vectors, lambda: s.get_vector(0)):
+                    try:
+                        call()
+                    except mv.MvfError:
+                        pass
+    assert opened > 0
