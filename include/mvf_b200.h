@@ -249,6 +249,12 @@ MVF_API int mvf_gpu_search_device(mvf_gpu_space* s, const void* d_queries, int q
  * on (padded to 128 queries x 256 rows tiles); out holds out_elems floats */
 MVF_API int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq, uint32_t k,
                             int metric, float* out, uint64_t out_elems, uint32_t* out_rows, uint32_t* out_cols);
+/* Diagnostic, host arithmetic only (no GPU needed): the launch shape the tensor-core kernel would use for nq
+ * queries, top-k, n resident rows of `dimension` elements (Float16, Int8 or UInt8) on a GPU with sm_count SMs.
+ * out16 = { query tiles, database tiles, runs ("chunks"), tiles per run, cluster size, query-tile groups, work items,
+ * grid, K blocks, candidate buffer entries, compaction trigger, pacing window, epilogue warpgroups, ring stages,
+ * pair form (0/1), dynamic shared memory bytes }.  Lets the CPU test-suite check the planner's invariants. */
+MVF_API int mvf_tc_plan(int data_type, uint32_t nq, uint32_t k, uint64_t n, uint32_t dimension, int sm_count, uint32_t* out16);
 /* path selection: 0 auto, 1 bandwidth scan (K1), 2 tensor-core contraction (K2) */
 MVF_API int mvf_gpu_set_path(mvf_gpu* g, int path);
 /* instrumentation: when enabled, searches bracket the dominant kernel with CUDA events on the

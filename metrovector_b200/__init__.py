@@ -151,6 +151,7 @@ _SIGS = {
     "mvf_gpu_space_get_vectors": [_P, _P, _U32, _INT, _P],
     "mvf_gpu_tc_dump": [_P, _P, _INT, _U32, _U32, _INT, _P, _U64, _c.POINTER(_U32), _c.POINTER(_U32)],
     "mvf_gpu_set_path": [_P, _INT],
+    "mvf_tc_plan": [_INT, _U32, _U32, _U64, _U32, _INT, _P],
     "mvf_gpu_profile": [_P, _INT],
     "mvf_gpu_profile_read": [_P, _c.POINTER(_c.c_double), _c.POINTER(_U64), _c.POINTER(_U64), _c.POINTER(_INT)],
     "mvf_gpu_synchronize": [_P],
@@ -159,6 +160,17 @@ _SIGS = {
 for _name, _args in _SIGS.items():
     getattr(_lib, _name).restype = _INT
     getattr(_lib, _name).argtypes = _args
+
+
+TC_PLAN_FIELDS = ("mtiles", "ntiles", "chunks", "tiles_per_chunk", "cluster", "mgroups", "items", "grid", "kblocks", "cap",
+                  "trigger", "sync_window", "epi_groups", "stages", "pair", "smem")
+
+
+def tc_plan(data_type, nq, k, n, dimension, sm_count=148):
+    """Launch shape of the tensor-core kernel for this problem (host arithmetic only, no GPU needed)."""
+    out = (_c.c_uint32 * 16)()
+    _check(_lib.mvf_tc_plan(int(data_type), nq, k, n, dimension, sm_count, out))
+    return dict(zip(TC_PLAN_FIELDS, [int(v) for v in out]))
 
 
 def filter_range_bitmap(column, data_type, lo, hi):

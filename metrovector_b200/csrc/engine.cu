@@ -1012,6 +1012,26 @@ int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint
     });
 }
 
+// Host-only planning query: the launch shape K2 would use for this problem on a GPU with `sm_count` SMs.
+// out[0..15] = mtiles, ntiles, chunks, tiles_per_chunk, cluster, mgroups, items, grid, kblocks, cap, trigger,
+// sync_window, epilogue groups, stages, pair form (0/1), dynamic shared memory bytes.  No CUDA call is made.
+int mvf_tc_plan(int data_type, uint32_t nq, uint32_t k, uint64_t n, uint32_t dimension, int sm_count, uint32_t* out16) {
+    return guard([&] {
+        if (!out16 || sm_count < 2 || nq == 0 || k == 0 || k > 128 || n == 0 || dimension == 0 ||
+            (data_type != k::DT_F16 && data_type != k::DT_I8 && data_type != k::DT_U8))
+            throw MvfError::build_error("no tensor-core plan for these arguments");
+        mvf::tc::TcState st;
+        mvf::tc::read_env(st);
+        const uint32_t es = data_type == k::DT_F16 ? 2 : 1;
+        const uint32_t pitch = (dimension * es + 15u) & ~15u;
+        const mvf::tc::Plan pl = mvf::tc::make_plan(st, data_type, nq, k, n, dimension, pitch, sm_count);
+        const uint32_t v[16] = {pl.mtiles, pl.ntiles, pl.chunks, pl.tiles_per_chunk, pl.CL, pl.mgroups, pl.items, pl.grid, pl.kblocks,
+                                pl.cap, pl.trigger, pl.sync_window, (uint32_t)pl.EG, (uint32_t)pl.stages, pl.pair ? 1u : 0u,
+                                (uint32_t)pl.smem};
+        for (int i = 0; i < 16; i++) out16[i] = v[i];
+    });
+}
+
 int mvf_gpu_set_path(mvf_gpu* g, int path) {
     return guard([&] { EngineLock engine_lock(g->mu);
         if (path < 0 || path > 2) throw MvfError::build_error("path must be 0 (auto), 1 (scan) or 2 (tensor)");

@@ -53,6 +53,7 @@ struct TcState {
     // uint8 128-d rows: dp4a keeps the scan ahead up to ~7 queries.  MVF_TC_MIN_BATCH overrides both.
     int min_batch_f16 = 4, min_batch_i8 = 8;
     bool attr_set = false;
+    bool env_read = false;
 };
 
 struct SearchArgs {
@@ -65,13 +66,10 @@ struct SearchResult {
     const u64* lists; uint32_t chunks; const float* qconst; const float* dump; uint32_t dump_cols; uint64_t launches;
 };
 
-inline void init(TcState& st) {
-    if (st.encode) return;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || !fn) { cudaGetLastError(); throw MvfError::cuda("cuTensorMapEncodeTiled is not available from the driver"); }
-    st.encode = (EncodeTiledFn)fn;
+// tuning knobs from the environment (host only; read when the engine is created so that path selection sees them)
+inline void read_env(TcState& st) {
+    if (st.env_read) return;
+    st.env_read = true;
     if (const char* c = std::getenv("MVF_TC_MIN_BATCH")) st.min_batch_f16 = st.min_batch_i8 = std::max(1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_CLUSTER")) st.cluster = std::atoi(c) == 1 ? 1 : 2;
     if (const char* c = std::getenv("MVF_TC_ITEMS_PER_SM")) st.items_per_sm = std::max(1, std::min(64, std::atoi(c)));
@@ -79,6 +77,15 @@ inline void init(TcState& st) {
     if (const char* c = std::getenv("MVF_TC_SYNC_WINDOW")) st.sync_window = std::max(-1, std::atoi(c));
     if (const char* c = std::getenv("MVF_TC_EPI_GROUPS")) st.epi_groups = std::atoi(c) == 4 ? 4 : (std::atoi(c) == 2 ? 2 : 0);
     if (const char* c = std::getenv("MVF_TC_PREFETCH")) st.l2_prefetch = std::max(0, std::min(4, std::atoi(c)));
+}
+inline void init(TcState& st) {
+    read_env(st);
+    if (st.encode) return;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { cudaGetLastError(); throw MvfError::cuda("cuTensorMapEncodeTiled is not available from the driver"); }
+    st.encode = (EncodeTiledFn)fn;
 }
 
 // shared memory: operand ring + per-warp sort scratch + per-warp column parameters + barriers
@@ -152,31 +159,62 @@ inline void make_map(TcState& st, CUtensorMap* map, const void* base, int dtype,
     if (r != CUDA_SUCCESS) throw MvfError::cuda("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
-inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_count) {
-    init(st);
-    const bool is_int = a.dtype != k::DT_F16;
-    const uint32_t es = is_int ? 1 : 2;
-    const uint32_t qpitch = (a.d * es + 15u) & ~15u;
-    const uint32_t mtiles = (a.nq + BM - 1) / BM;
-    const uint32_t ntiles = (uint32_t)((a.n + BN - 1) / BN);
+// Everything the launch is shaped by, as plain host arithmetic (no CUDA calls), so the planner can be checked on a
+// machine without a GPU (mvf_tc_plan in the C ABI, tests/test_tc_plan.py).
+struct Plan {
+    uint32_t mtiles, ntiles, chunks, tiles_per_chunk, CL, mgroups, items, grid, kblocks, cap, trigger, sync_window, qpitch;
+    int EG, stages;
+    bool pair, is_int;
+    size_t smem;
+};
+inline Plan make_plan(const TcState& st, int dtype, uint32_t nq, uint32_t kk, uint64_t n, uint32_t d, uint32_t pitch, int sm_count) {
+    Plan pl;
+    pl.is_int = dtype != k::DT_F16;
+    const uint32_t es = pl.is_int ? 1 : 2;
+    pl.qpitch = (d * es + 15u) & ~15u;
+    pl.mtiles = (nq + BM - 1) / BM;
+    pl.ntiles = (uint32_t)((n + BN - 1) / BN);
     // work items = (query tile, contiguous run of database tiles); ~8 items per SM, each item keeps
     // its own running thresholds, the item lists are merged afterwards
-    uint32_t chunks = std::max<uint32_t>(1, ((uint32_t)st.items_per_sm * (uint32_t)sm_count + mtiles - 1) / mtiles);
-    chunks = std::min(chunks, ntiles);
-    const uint32_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
-    chunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
-    const uint32_t CL = (st.cluster == 2 && mtiles >= 2) ? 2u : 1u;
-    const uint32_t mgroups = (mtiles + CL - 1) / CL;
-    const uint32_t items = mgroups * chunks;
-    const uint32_t grid = std::min<uint32_t>((uint32_t)sm_count / CL, items) * CL;
-    const uint32_t kblocks = (a.d * es + BKB - 1) / BKB;
-    int EG = st.epi_groups ? st.epi_groups : (kblocks <= 2 ? 4 : 2);
-    uint32_t cap = cap_for_k(a.k, EG);
+    uint32_t chunks = std::max<uint32_t>(1, ((uint32_t)st.items_per_sm * (uint32_t)sm_count + pl.mtiles - 1) / pl.mtiles);
+    chunks = std::max<uint32_t>(1, std::min(chunks, pl.ntiles));
+    pl.tiles_per_chunk = (pl.ntiles + chunks - 1) / chunks;
+    pl.chunks = (pl.ntiles + pl.tiles_per_chunk - 1) / pl.tiles_per_chunk;
+    pl.CL = (st.cluster == 2 && pl.mtiles >= 2) ? 2u : 1u;
+    pl.mgroups = (pl.mtiles + pl.CL - 1) / pl.CL;
+    pl.items = pl.mgroups * pl.chunks;
+    pl.grid = std::min<uint32_t>((uint32_t)sm_count / pl.CL, pl.items) * pl.CL;
+    pl.kblocks = (d * es + BKB - 1) / BKB;
+    pl.EG = st.epi_groups ? st.epi_groups : (pl.kblocks <= 2 ? 4 : 2);
+    pl.cap = cap_for_k(kk, pl.EG);
     // short rows are bound by the epilogue, and a pair's leader waits for the slower of two epilogues (measured on
     // config E batched: 840 -> 620 TOP/s), so the pair form is for rows of more than two K blocks (MVF_TC_PAIR=2 forces it)
-    const bool pair = CL == 2 && (st.pair == 2 || (st.pair == 1 && kblocks > 2));
-    if (EG == 4 && smem_bytes(cap, EG, 3, pair) > 227 * 1024) { EG = 2; cap = cap_for_k(a.k, EG); }
-    const int stages = stages_for(cap, EG, pair);
+    pl.pair = pl.CL == 2 && (st.pair == 2 || (st.pair == 1 && pl.kblocks > 2));
+    if (pl.EG == 4 && smem_bytes(pl.cap, pl.EG, 3, pl.pair) > 227 * 1024) { pl.EG = 2; pl.cap = cap_for_k(kk, pl.EG); }
+    pl.stages = stages_for(pl.cap, pl.EG, pl.pair);
+    pl.trigger = std::min<uint32_t>(trigger_for_k(kk), pl.cap - (uint32_t)(BN / pl.EG));
+    pl.smem = smem_bytes(pl.cap, pl.EG, pl.stages, pl.pair);
+    // pacing window (tiles a producer may lead the slowest item on the same rows): sized so that the tiles "in
+    // flight" across all concurrently processed runs stay around 16 MB of L2 -- 9 tiles of 393 KB for config C
+    // (4.6 runs at a time), 2 for D batch 1024 (18.5 runs; measured 1 105 vs 1 075 TFLOP/s at 8), dozens for 32 KB tiles
+    pl.sync_window = 0;
+    if (st.sync_window >= 0) pl.sync_window = (uint32_t)st.sync_window;
+    else if (pl.mgroups >= 2) {
+        const double runs = std::max(1.0, (double)(pl.grid / pl.CL) / (double)pl.mgroups);
+        const double tile_bytes = (double)BN * (double)pitch;
+        pl.sync_window = (uint32_t)std::min(64.0, std::max(2.0, 16.0 * 1048576.0 / (runs * tile_bytes)));
+    }
+    return pl;
+}
+
+inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_count) {
+    init(st);
+    const Plan pl = make_plan(st, a.dtype, a.nq, a.k, a.n, a.d, a.pitch, sm_count);
+    const bool is_int = pl.is_int, pair = pl.pair;
+    const uint32_t qpitch = pl.qpitch, mtiles = pl.mtiles, ntiles = pl.ntiles, chunks = pl.chunks, tiles_per_chunk = pl.tiles_per_chunk;
+    const uint32_t CL = pl.CL, mgroups = pl.mgroups, items = pl.items, grid = pl.grid, kblocks = pl.kblocks, cap = pl.cap;
+    const uint32_t sync_window = pl.sync_window;
+    const int EG = pl.EG, stages = pl.stages;
 
     st.qprep.reserve((size_t)mtiles * BM * qpitch);
     st.qconst.reserve((size_t)a.nq * 4);
@@ -184,16 +222,6 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     st.lists.reserve((size_t)a.nq * chunks * EG * a.k * 8);
     st.gthr.reserve((size_t)mgroups * CL * BM * 4);
     TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mgroups * CL * BM * 4, stream));
-    // pacing window (tiles a producer may lead the slowest item on the same rows): sized so that the tiles "in
-    // flight" across all concurrently processed runs stay around 16 MB of L2 -- 8 tiles of 393 KB for config C
-    // (4.6 runs at a time), 2 for D batch 1024 (18.5 runs; measured 1 105 vs 1 075 TFLOP/s at 8), dozens for 32 KB tiles
-    uint32_t sync_window = 0;
-    if (st.sync_window >= 0) sync_window = (uint32_t)st.sync_window;
-    else if (mgroups >= 2) {
-        const double runs = std::max(1.0, (double)(grid / CL) / (double)mgroups);
-        const double tile_bytes = (double)BN * (double)a.pitch;
-        sync_window = (uint32_t)std::min(64.0, std::max(2.0, 16.0 * 1048576.0 / (runs * tile_bytes)));
-    }
     if (sync_window) {
         st.progress.reserve((size_t)items * 4);
         TC_CUDA_CHECK(cudaMemsetAsync(st.progress.p, 0, (size_t)items * 4, stream));
@@ -219,7 +247,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
-    p.trigger = std::min<uint32_t>(trigger_for_k(a.k), cap - (uint32_t)(BN / EG));
+    p.trigger = pl.trigger;
     p.kblocks = kblocks;
     p.mtiles = mtiles; p.ntiles = ntiles; p.chunks = chunks; p.tiles_per_chunk = tiles_per_chunk;
     p.metric = a.metric; p.is_int = is_int ? 1 : 0;
@@ -243,7 +271,7 @@ inline SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, i
     }
     const bool l2 = a.metric == k::M_L2;
     const void* fn = select_kernel(is_int, l2, (int)CL, EG, pair);
-    const size_t smem = smem_bytes(cap, EG, stages, pair);
+    const size_t smem = pl.smem;
     TC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&map_q, (void*)&map_x, (void*)&p};
     cudaLaunchConfig_t cfg = {};
