@@ -237,7 +237,12 @@ MVF_API int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uin
  * UINT64_MAX): out_ids = ScoredVector.index; out_scores = ScoredVector.score (L2 distance for
  * float spaces, squared distance for integer spaces, dot for InnerProduct, 1-cos for Cosine);
  * out_iscores (may be NULL) = exact int32 score for integer spaces with L2/InnerProduct.
- * With a communicator every rank must call it with the same queries; every rank gets the result. */
+ * With a communicator every rank must call it with the same queries; every rank gets the result.
+ * Limits of this build (each answered with MVF_ERR_BUILD, never with a wrong result): a resident space holds
+ * fewer than 2^32 rows; a row is at most 1 MiB; integer spaces have dimension <= 33025 (int32 accumulation,
+ * SURVEY.md 8a); the per-CTA candidate lists of the scan kernel live in shared memory, so k is bounded by
+ * 8 * pow2(8k) + dimension * 4 (or * 1 for integer spaces) <= ~227 KB, i.e. k <= 2048 for rows up to 24 KB;
+ * the tensor-core path is taken for k <= 128 only (larger k run on the scan kernel). */
 MVF_API int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq,
                            uint32_t k, int metric, uint64_t* out_ids, float* out_scores,
                            int32_t* out_iscores);
