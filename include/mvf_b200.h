@@ -17,8 +17,9 @@
  *   - handles are opaque.  mvf_space* and row pointers borrow from their mvf_file and die with
  *     it (src/vectors/vector_space.rs:34-39).  mvf_gpu_space* owns its HBM copy and outlives
  *     the file it was uploaded from.
- *   - file/space handles are immutable and thread-safe (src/reader.rs:284-289); searches on one
- *     mvf_gpu are serialised by the caller (one stream + scratch per engine).
+ *   - file/space handles are immutable and thread-safe (src/reader.rs:284-289); every entry point that
+ *     touches an engine's stream or scratch takes the engine's lock, so calls on one mvf_gpu from several
+ *     host threads are serialised by the library (one stream + scratch per device).
  */
 #ifndef MVF_B200_H
 #define MVF_B200_H
@@ -65,10 +66,15 @@ typedef enum mvf_distance_metric {
 typedef struct mvf_file mvf_file;           /* MvfReader / "MvfFile"   src/reader.rs:27-31   */
 typedef struct mvf_space mvf_space;         /* VectorSpace<'a>         src/vectors/vector_space.rs:34-39 */
 typedef struct mvf_builder mvf_builder;     /* MvfBuilder              src/builder.rs:93-98  */
-typedef struct mvf_gpu mvf_gpu;             /* one engine = one process on one B200 (new) */
+typedef struct mvf_gpu mvf_gpu;             /* the search engine on one B200, or on several from one process (new) */
 typedef struct mvf_gpu_space mvf_gpu_space; /* HBM-resident shard of one vector space (new) */
 
 MVF_API const char* mvf_last_error(void);
+/* The two numbers of the reference's structured error variants for the last failing call on this thread, in
+ * declaration order (src/errors.rs:15-31): UnsupportedVersion{got, expected}, IndexOutOfBounds{index, len},
+ * DimensionMismatch{expected, actual}, InvalidVectorType{expected, actual} (VectorType values); 0, 0 otherwise.
+ * With them a binding rebuilds every MvfError variant exactly. */
+MVF_API void mvf_last_error_fields(uint64_t* first, uint64_t* second);
 MVF_API const char* mvf_version_string(void);
 
 /* ---------------------------------------------------------------- reader (src/reader.rs) -- */
@@ -168,8 +174,17 @@ MVF_API int mvf_builder_set_vector_ids(mvf_builder* b, const char* space, const 
 MVF_API int mvf_builder_save(mvf_builder* b, const char* path);
 
 /* ---------------------------------------------------------------- GPU engine (new) ------- */
-/* one engine per process, bound to one device.  Fails with MVF_ERR_CUDA when no sm_100 GPU. */
+/* An engine bound to one device.  Fails with MVF_ERR_CUDA when no sm_100 GPU. */
 MVF_API int mvf_gpu_init(int device, mvf_gpu** out);
+/* ONE process, n devices: the engine behind a single call site of find_top_k_similar (examples/similarity_search.rs:117)
+ * that uses every GPU of the box.  Spaces created on it are row-sharded over the devices (mvf_shard_range), a search
+ * runs the shards' kernels concurrently, exchanges the local top-k with one ncclAllGather per device (communicator
+ * from ncclCommInitAll) and merges on devices[0].  n = 1 gives a plain single-device engine.  mvf_gpu_set_stream,
+ * mvf_gpu_comm_init and mvf_gpu_tc_dump are single-device calls and answer MVF_ERR_BUILD on such an engine;
+ * mvf_gpu_search_device takes pointers into devices[0]'s memory. */
+MVF_API int mvf_gpu_init_multi(const int* devices, int n, mvf_gpu** out);
+/* devices this engine spans (1 for mvf_gpu_init) */
+MVF_API int mvf_gpu_device_count(const mvf_gpu* g, int* out);
 MVF_API void mvf_gpu_shutdown(mvf_gpu* g);
 /* run every search of this engine on the caller's CUDA stream (cudaStream_t as void*) */
 MVF_API int mvf_gpu_set_stream(mvf_gpu* g, void* cuda_stream);
@@ -209,9 +224,17 @@ MVF_API int mvf_gpu_space_set_tombstones(mvf_gpu_space* s, const uint8_t* bitmap
 MVF_API int mvf_gpu_space_set_ids(mvf_gpu_space* s, const uint64_t* ids, uint64_t count);
 MVF_API int mvf_gpu_space_info(const mvf_gpu_space* s, uint64_t* local_n, uint64_t* row_base,
                                uint64_t* global_n, uint32_t* dimension, int* data_type, int* metric);
+/* What the scan-vs-tensor choice depends on besides the shape (identical on every rank of a sharded space):
+ * rows holding Inf/NaN components over all shards (float spaces with any stay on the scan kernel, whose
+ * element-wise arithmetic defines the result), whether the split-tf32 operand planes of a Float32 space are
+ * resident on every shard, and the row count the choice is taken on (the smallest non-empty shard). */
+MVF_API int mvf_gpu_space_path_facts(const mvf_gpu_space* s, uint64_t* nonfinite_rows, int* tf32_planes_resident,
+                                     uint64_t* decision_rows);
 /* how the rows got to HBM: path 1 = cudaHostRegister'd mapping, 2 = pinned staging, 0 = generated */
 MVF_API int mvf_gpu_space_upload_stats(const mvf_gpu_space* s, int* path, double* seconds, uint64_t* bytes);
-/* diagnostic: why the mapping was not page-locked in place (empty string when it was, or for generated spaces) */
+/* diagnostic: which in-place registration variants were tried ("ro" = cudaHostRegisterReadOnly on the reader's
+ * mapping, "rw" = cudaHostRegisterDefault on it, "private" = a copy-on-write re-mapping of the file range), which
+ * the driver refused and with what error, and which one was accepted (empty for generated spaces) */
 MVF_API const char* mvf_gpu_space_upload_note(const mvf_gpu_space* s);
 /* copy rows / norms back (tests: device bytes == mapped bytes) */
 MVF_API int mvf_gpu_space_read_rows(const mvf_gpu_space* s, uint64_t local_start, uint64_t count, void* out);
@@ -220,6 +243,8 @@ MVF_API int mvf_gpu_space_read_norms(const mvf_gpu_space* s, float* out_norm, fl
 /* Integrity (the finished intent of MvfReader::validate_with_checksum, src/reader.rs:172-221, on the
  * device): CRC-32/IEEE of the resident rows computed by a CUDA kernel; _verify compares it with the
  * block manifest entry the builder wrote (src/builder.rs:251) -> MVF_ERR_CORRUPTED_DATA on mismatch. */
+/* Sharded spaces: every shard hashes its rows, shard CRCs are combined with the crc32_combine identity (under a
+ * communicator the call is a collective: every rank calls it and receives the CRC of the whole block). */
 MVF_API int mvf_gpu_space_checksum(mvf_gpu_space* s, uint32_t* out_crc, double* out_kernel_ms);
 MVF_API int mvf_gpu_space_verify_checksum(mvf_gpu_space* s, const mvf_space* file_space);
 
@@ -242,11 +267,13 @@ MVF_API int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uin
  * fewer than 2^32 rows; a row is at most 1 MiB; integer spaces have dimension <= 33025 (int32 accumulation,
  * SURVEY.md 8a); the per-CTA candidate lists of the scan kernel live in shared memory, so k is bounded by
  * 8 * pow2(8k) + dimension * 4 (or * 1 for integer spaces) <= ~227 KB, i.e. k <= 2048 for rows up to 24 KB;
- * the tensor-core path is taken for k <= 128 only (larger k run on the scan kernel). */
+ * the tensor-core path is taken for k <= 128 only (larger k run on the scan kernel).
+ * Float spaces holding Inf/NaN rows, and batches holding Inf/NaN queries, always run on the scan kernel. */
 MVF_API int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq,
                            uint32_t k, int metric, uint64_t* out_ids, float* out_scores,
                            int32_t* out_iscores);
-/* same with DEVICE pointers, asynchronous on the engine stream (no host sync) */
+/* same with DEVICE pointers, asynchronous on the engine stream.  One exception: a float batch that qualifies for
+ * the tensor path is first checked for Inf/NaN on the device, which costs one stream synchronisation (~10 us). */
 MVF_API int mvf_gpu_search_device(mvf_gpu_space* s, const void* d_queries, int query_dtype,
                                   uint32_t nq, uint32_t k, int metric, uint64_t* d_out_ids,
                                   float* d_out_scores, int32_t* d_out_iscores);

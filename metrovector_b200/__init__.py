@@ -120,6 +120,9 @@ _SIGS = {
     "mvf_builder_add_metadata_column": [_P, _c.c_char_p, _INT, _P, _SZ],
     "mvf_builder_save": [_P, _c.c_char_p],
     "mvf_gpu_init": [_INT, _c.POINTER(_P)],
+    "mvf_gpu_init_multi": [_c.POINTER(_INT), _INT, _c.POINTER(_P)],
+    "mvf_gpu_device_count": [_P, _c.POINTER(_INT)],
+    "mvf_gpu_space_path_facts": [_P, _c.POINTER(_U64), _c.POINTER(_INT), _c.POINTER(_U64)],
     "mvf_gpu_set_stream": [_P, _P],
     "mvf_gpu_device_info": [_P, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_U64), _c.POINTER(_U64)],
     "mvf_gpu_comm_unique_id": [_P],
@@ -184,10 +187,18 @@ def filter_range_bitmap(column, data_type, lo, hi):
     return np.unpackbits(out, bitorder="little")[:n].astype(bool)
 
 
+_lib.mvf_last_error_fields.restype = None
+_lib.mvf_last_error_fields.argtypes = [_c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]
+
+
 def _check(rc):
     if rc != 0:
         msg = (_lib.mvf_last_error() or b"").decode("utf-8", "replace")
-        raise _ERRORS.get(rc, MvfError)(msg)
+        a, b = _c.c_uint64(), _c.c_uint64()
+        _lib.mvf_last_error_fields(_c.byref(a), _c.byref(b))
+        err = _ERRORS.get(rc, MvfError)(msg)
+        err.fields = (a.value, b.value)        # (got, expected) / (index, len) / (expected, actual) of the structured variants
+        raise err
 
 
 def version_string():
@@ -462,13 +473,24 @@ ScoredVector = namedtuple("ScoredVector", ["index", "score"])    # similarity_se
 
 
 class GpuEngine:
-    """One engine per process, bound to one B200."""
+    """The search engine on one B200 (``GpuEngine(0)``) or, from one process, on several (``GpuEngine([0, 1, ...])``:
+    spaces are row-sharded over the devices and every search uses all of them)."""
 
     def __init__(self, device=0):
         self._h = _P()
-        _check(_lib.mvf_gpu_init(device, _c.byref(self._h)))
-        self.device = device
+        if isinstance(device, (list, tuple)):
+            devs = (_INT * len(device))(*[int(x) for x in device])
+            _check(_lib.mvf_gpu_init_multi(devs, len(device), _c.byref(self._h)))
+            self.device = int(device[0]) if device else 0
+        else:
+            _check(_lib.mvf_gpu_init(device, _c.byref(self._h)))
+            self.device = device
         self.rank, self.world = 0, 1
+
+    def device_count(self):
+        n = _INT()
+        _check(_lib.mvf_gpu_device_count(self._h, _c.byref(n)))
+        return n.value
 
     def shutdown(self):
         if getattr(self, "_h", None):
@@ -546,6 +568,12 @@ class GpuSpace:
 
     def __del__(self):
         self.free()
+
+    def path_facts(self):
+        """What the scan-vs-tensor choice depends on besides the shape (same on every rank of a sharded space)."""
+        nf, sp, dr = _U64(), _INT(), _U64()
+        _check(_lib.mvf_gpu_space_path_facts(self._h, _c.byref(nf), _c.byref(sp), _c.byref(dr)))
+        return dict(nonfinite_rows=nf.value, tf32_planes=bool(sp.value), decision_rows=dr.value)
 
     def upload_stats(self):
         p, s, b = _INT(), _c.c_double(), _U64()

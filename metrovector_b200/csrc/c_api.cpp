@@ -9,7 +9,8 @@
 
 namespace mvf {
 thread_local std::string g_last_error;
-void set_last_error(const std::string& m) { g_last_error = m; }
+thread_local uint64_t g_last_fields[2] = {0, 0};
+void set_last_error(const std::string& m, uint64_t first, uint64_t second) { g_last_error = m; g_last_fields[0] = first; g_last_fields[1] = second; }
 }  // namespace mvf
 
 using namespace mvf;
@@ -20,6 +21,10 @@ struct mvf_builder { MvfBuilder b; };
 extern "C" {
 
 const char* mvf_last_error(void) { return g_last_error.c_str(); }
+void mvf_last_error_fields(uint64_t* first, uint64_t* second) {
+    if (first) *first = g_last_fields[0];
+    if (second) *second = g_last_fields[1];
+}
 const char* mvf_version_string(void) { return "mvf_b200 0.1 (sm_100a)"; }
 
 int mvf_file_open(const char* path, mvf_file** out) {

@@ -11,7 +11,7 @@ struct mvf_space { mvf::VectorSpace vs; };
 
 namespace mvf {
 
-void set_last_error(const std::string& m);
+void set_last_error(const std::string& m, uint64_t first = 0, uint64_t second = 0);
 
 // run `fn`, translate any exception into a status code + thread-local message
 template <class Fn>
@@ -20,7 +20,7 @@ inline int guard(Fn&& fn) noexcept {
         fn();
         return MVF_OK;
     } catch (const MvfError& e) {
-        set_last_error(e.what());
+        set_last_error(e.what(), e.first, e.second);
         return (int)e.kind;
     } catch (const std::bad_alloc&) {
         set_last_error("I/O error: out of host memory");

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) merge_topk_warp(const MergeParams p, uint
 // ------------------------------------------------------------------------------------------------
 template <int DT>
 __global__ void __launch_bounds__(256) row_norms(const unsigned char* rows, uint64_t n, uint32_t pitch, float* norm,
-                                                  float* sq) {
+                                                  float* sq, unsigned long long* nonfinite) {
     constexpr int EPC = Traits<DT>::EPC;
     const int lane = threadIdx.x & 31;
     const uint32_t C = pitch >> 4;
@@ -363,7 +363,12 @@ __global__ void __launch_bounds__(256) row_norms(const unsigned char* rows, uint
             is += __shfl_xor_sync(0xffffffffu, is, off);
         }
         if (lane == 0) {
-            if (Traits<DT>::is_float) { norm[row] = __fsqrt_rn(fs); sq[row] = fs; }
+            if (Traits<DT>::is_float) {
+                norm[row] = __fsqrt_rn(fs); sq[row] = fs;
+                // rows holding Inf/NaN (or whose |x|^2 overflows f32): the space then stays on the scan kernel, whose
+                // element-wise arithmetic defines the result for such rows (DESIGN.md "non-finite values")
+                if (nonfinite != nullptr && !(fabsf(fs) <= 3.402823466e38f)) atomicAdd(nonfinite, 1ull);
+            }
             else { norm[row] = __fsqrt_rn((float)is); reinterpret_cast<int*>(sq)[row] = is; }
         }
     }
@@ -378,7 +383,8 @@ __global__ void __launch_bounds__(256) row_norms(const unsigned char* rows, uint
 // contributions are XOR-ed together.
 // ------------------------------------------------------------------------------------------------
 struct CrcParams {
-    const unsigned char* data; uint64_t nbytes; uint64_t seg_len;   // seg_len: multiple of 16
+    const unsigned char* data; uint64_t nbytes; uint64_t seg_len;   // message bytes; bytes per segment (thread)
+    uint64_t seg_stride;         // bytes between segment starts in memory (== seg_len for contiguous rows, the row pitch otherwise); multiple of 16
     const uint32_t* tables;      // [8][256] slicing tables
     const uint32_t* x2n;         // [64] x^(2^k) mod P, reflected representation
     uint32_t* out;               // XOR accumulator, zeroed by the caller
@@ -398,6 +404,16 @@ __device__ __forceinline__ uint32_t crc_step8(const uint32_t (*T)[256], uint32_t
            T[3][b & 0xff] ^ T[2][(b >> 8) & 0xff] ^ T[1][(b >> 16) & 0xff] ^ T[0][b >> 24];
 }
 #ifdef MVF_ENGINE_TU
+// sets *flag when any of `count` f16 / f32 values is Inf or NaN (exponent all ones): such query batches stay on the
+// scan kernel (DESIGN.md "non-finite values")
+__global__ void __launch_bounds__(256) flag_nonfinite(const void* data, uint64_t count, int is_f16, uint32_t* flag) {
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (is_f16) bad |= (reinterpret_cast<const unsigned short*>(data)[i] & 0x7c00u) == 0x7c00u;
+        else bad |= (reinterpret_cast<const uint32_t*>(data)[i] & 0x7f800000u) == 0x7f800000u;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
 __global__ void __launch_bounds__(256) crc32_resident(const CrcParams p) {
     __shared__ uint32_t T[8][256];
     for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&T[0][0])[i] = p.tables[i];
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(256) crc32_resident(const CrcParams p) {
     uint32_t contrib = 0;
     if (off < p.nbytes) {
         const uint64_t len = min(p.seg_len, p.nbytes - off);
-        const unsigned char* s = p.data + off;
+        const unsigned char* s = p.data + t * p.seg_stride;
         uint32_t crc = 0xffffffffu;
         uint64_t i = 0;
         for (; i + 128 <= len; i += 128) {                  // one 128-byte line per iteration, 8 loads in flight

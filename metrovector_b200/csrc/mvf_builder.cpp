@@ -168,6 +168,19 @@ void MvfBuilder::set_vector_ids(const std::string& space, const uint64_t* ids, s
 }
 
 std::vector<uint8_t> MvfBuilder::to_bytes() const {
+    // side tables are checked against the rows present NOW: rows may have been added after set_vector_ids /
+    // set_tombstones, and a file whose id block is shorter than its space is rejected by every reader
+    for (const auto& s : spaces_) {
+        const size_t es = element_size(s.data_type);
+        const uint64_t total = (s.dimension && es) ? s.vectors.size() / ((uint64_t)s.dimension * es) : 0;
+        if (!s.vector_ids.empty() && s.vector_ids.size() / 8 != total) throw MvfError::dimension_mismatch(total, s.vector_ids.size() / 8);
+        if (!s.tombstones.empty() && (uint64_t)s.tombstones.size() * 8 < total)
+            throw MvfError::dimension_mismatch(total, (uint64_t)s.tombstones.size() * 8);
+        if (!s.tombstone_list.empty()) {
+            uint64_t last; std::memcpy(&last, s.tombstone_list.data() + s.tombstone_list.size() - 8, 8);
+            if (last >= total) throw MvfError::index_out_of_bounds(last, total);
+        }
+    }
     std::vector<uint8_t> out = {'M', 'V', 'F', '1'};
     std::vector<uint8_t> manifest;
     uint64_t cur = 0;
@@ -260,9 +273,14 @@ void MvfBuilder::save(const std::string& path) const {
     std::vector<uint8_t> bytes = to_bytes();
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) throw MvfError::io(std::string(std::strerror(errno)) + " (" + path + ")");
-    size_t w = std::fwrite(bytes.data(), 1, bytes.size(), f);
-    int e = errno;
-    if (std::fclose(f) != 0 || w != bytes.size()) throw MvfError::io(std::strerror(e));
+    errno = 0;
+    const size_t w = std::fwrite(bytes.data(), 1, bytes.size(), f);
+    if (w != bytes.size()) {
+        const int e = errno;                         // of the failing fwrite, before fclose can overwrite it
+        std::fclose(f);
+        throw MvfError::io(std::string(e ? std::strerror(e) : "short write") + " (" + path + ")");
+    }
+    if (std::fclose(f) != 0) { const int e = errno; throw MvfError::io(std::string(std::strerror(e)) + " (" + path + ")"); }
 }
 
 }  // namespace mvf

@@ -24,22 +24,26 @@ enum class ErrorKind : int {
 
 class MvfError : public std::runtime_error {
 public:
-    MvfError(ErrorKind k, const std::string& msg) : std::runtime_error(msg), kind(k) {}
+    MvfError(ErrorKind k, const std::string& msg, uint64_t a = 0, uint64_t b = 0) : std::runtime_error(msg), kind(k), first(a), second(b) {}
     ErrorKind kind;
+    // the two fields of the reference's structured variants, in declaration order (src/errors.rs:15-31):
+    // UnsupportedVersion{got, expected}, IndexOutOfBounds{index, len}, DimensionMismatch{expected, actual},
+    // InvalidVectorType{expected, actual}; 0 for the string variants
+    uint64_t first, second;
     // constructors producing the reference's Display strings (src/errors.rs:9-39)
     static MvfError io(const std::string& m) { return {ErrorKind::Io, "I/O error: " + m}; }
     static MvfError invalid_format(const std::string& m) { return {ErrorKind::InvalidFormat, "Invalid file format: " + m}; }
     static MvfError unsupported_version(unsigned got, unsigned expected) {
         return {ErrorKind::UnsupportedVersion,
-                "Unsupported version: got " + std::to_string(got) + ", expected " + std::to_string(expected)};
+                "Unsupported version: got " + std::to_string(got) + ", expected " + std::to_string(expected), got, expected};
     }
     static MvfError space_not_found(const std::string& n) { return {ErrorKind::VectorSpaceNotFound, "Vector space '" + n + "' not found"}; }
     static MvfError index_out_of_bounds(uint64_t index, uint64_t len) {
-        return {ErrorKind::IndexOutOfBounds, "Index out of bounds: " + std::to_string(index) + " >= " + std::to_string(len)};
+        return {ErrorKind::IndexOutOfBounds, "Index out of bounds: " + std::to_string(index) + " >= " + std::to_string(len), index, len};
     }
     static MvfError dimension_mismatch(uint64_t expected, uint64_t actual) {
         return {ErrorKind::DimensionMismatch,
-                "Dimension mismatch: expected " + std::to_string(expected) + ", got " + std::to_string(actual)};
+                "Dimension mismatch: expected " + std::to_string(expected) + ", got " + std::to_string(actual), expected, actual};
     }
     static MvfError corrupted_data(const std::string& m) { return {ErrorKind::CorruptedData, "Corrupted data: " + m}; }
     static MvfError build_error(const std::string& m) { return {ErrorKind::Build, "Build error: " + m}; }
@@ -158,6 +162,7 @@ public:
     void validate() const;                                            // :149-162
     void validate_with_checksum() const;                              // :172-221 (intent)
     const uint8_t* data() const { return map_; }
+    int fd() const { return fd_; }                                    // the open descriptor behind the mapping (residency re-maps ranges of it)
     const std::vector<SpaceInfo>& spaces() const { return spaces_; }
     const std::vector<DataBlock>& blocks() const { return blocks_; }
 private:

@@ -53,19 +53,25 @@ uint16_t f32_to_f16(float f) {
     return out;
 }
 
-uint32_t crc32_ieee(const void* data, size_t n, uint32_t crc) {
-    static uint32_t table[8][256];
-    static bool init = false;
-    if (!init) {
+namespace {
+struct CrcTables {
+    uint32_t t[8][256];
+    CrcTables() {
         for (uint32_t i = 0; i < 256; i++) {
             uint32_t c = i;
             for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            table[0][i] = c;
+            t[0][i] = c;
         }
         for (uint32_t i = 0; i < 256; i++)
-            for (int t = 1; t < 8; t++) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
-        init = true;
+            for (int s = 1; s < 8; s++) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xff];
     }
+};
+}  // namespace
+
+uint32_t crc32_ieee(const void* data, size_t n, uint32_t crc) {
+    // function-local static: initialised exactly once even when the first calls race (file handles are thread-safe)
+    static const CrcTables tables;
+    const uint32_t (*table)[256] = tables.t;
     const uint8_t* p = (const uint8_t*)data;
     crc = ~crc;
     while (n >= 8) {   // slicing-by-8

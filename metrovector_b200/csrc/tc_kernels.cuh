@@ -27,25 +27,13 @@
 #include <stdint.h>
 
 #include "kernels.cuh"
+#include "tc_path.hpp"
 
 namespace mvf {
 namespace tc {
 
-using k::u64;
 using k::kInf;
-
-constexpr int BM = 128;            // queries per tile (TMEM lanes)
-constexpr int BN = 256;            // database rows per tile (TMEM columns, MMA N)
-constexpr int BKB = 128;           // K block in bytes (one 128-byte swizzle row)
-constexpr int MAX_STAGES = 6;
-constexpr int A_BYTES = BM * BKB;  // 16 KiB
-constexpr int B_BYTES = BN * BKB;  // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;           // one CTA holds the whole database tile
-constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES / 2;  // CTA pair (cta_group::2): each CTA holds half of it
-// epilogue warpgroups (template parameter EG = 2 or 4): each takes BN / EG columns of every tile.  Short rows
-// (K of one or two 128-byte blocks) leave only 512-1024 MMA cycles per tile, so they get 4 groups.
-constexpr int threads_for(int eg) { return 64 + 128 * eg; }
-constexpr int MAX_CAP = 512;       // candidate buffer entries per query (power of two)
+static_assert(BM == 128 && BN == 256 && BKB == 128, "tile shape the descriptors below are written for");
 
 struct TcParams {
     const float* norm;             // sqrt(sum x^2) per resident row
@@ -61,7 +49,7 @@ struct TcParams {
     uint32_t kblocks;              // ceil(d * elem / 128)
     uint32_t mtiles, ntiles, chunks, tiles_per_chunk;
     int metric;                    // k::M_L2 / M_IP / M_COS
-    int is_int;                    // 0: f16 operands / f32 accum, 1: int8 operands / s32 accum
+    int kind;                      // KIND_F16: f16 operands / f32 accum, KIND_I8: int8 / s32, KIND_TF32: two tf32 planes / f32
     uint32_t idesc;                // tcgen05 instruction descriptor
     uint32_t l2_prefetch_tiles;    // database tiles the producer prefetches into L2 ahead of its TMA loads (0 = off)
     uint32_t stages;               // depth of the operand ring (<= MAX_STAGES)
@@ -126,36 +114,25 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-template <bool INT>
+#define MVF_UMMA_ASM(GROUP, KINDSTR)                                                              \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                \
+                 "tcgen05.mma.cta_group::" GROUP ".kind::" KINDSTR " [%0], %1, %2, %3, p;\n\t}"     \
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory")
+template <int KIND>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (INT) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    }
+    if (KIND == KIND_I8) MVF_UMMA_ASM("1", "i8");
+    else if (KIND == KIND_TF32) MVF_UMMA_ASM("1", "tf32");
+    else MVF_UMMA_ASM("1", "f16");
 }
 // ---- CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a cluster, M = 256 (128 query rows per CTA),
 // each CTA supplies half of the B operand from its own shared memory ----
-template <bool INT>
+template <int KIND>
 __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (INT) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    }
+    if (KIND == KIND_I8) MVF_UMMA_ASM("2", "i8");
+    else if (KIND == KIND_TF32) MVF_UMMA_ASM("2", "tf32");
+    else MVF_UMMA_ASM("2", "f16");
 }
+#undef MVF_UMMA_ASM
 // arrives on the barrier at the same shared-memory offset in every CTA of `mask` once the pair's MMAs retire
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -275,12 +252,22 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // ring is 5-6 deep), the leader CTA issues, both epilogues drain their own TMEM.  Against the multicast form
 // this cuts the bytes written into each SM's shared memory per tile by a third and halves the tensor core's
 // shared-memory reads of the B operand.
-template <bool INT, int MODE, int CL, int EG, bool PAIR>
+// KIND_TF32 (K2', Float32 spaces): operands come as two tf32-exact planes (map_q/map_x = hi, map_q2/map_x2 = lo);
+// a stage holds [Q_hi | Q_lo | X_hi | X_lo] and every K step issues three MMAs (hi.hi, lo.hi, hi.lo), so the
+// accumulator carries q.x to ~2^-21 relative (the dropped lo.lo term) -- inside the float tolerance of the scan.
+template <int KIND, int MODE, int CL, int EG, bool PAIR>
 __global__ void __launch_bounds__(threads_for(EG), 1)
-gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
+gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+             const __grid_constant__ CUtensorMap map_q2, const __grid_constant__ CUtensorMap map_x2, const TcParams p) {
     static_assert(!PAIR || CL == 2, "the pair form needs clusters of two");
+    static_assert(KIND != KIND_TF32 || PAIR || CL == 1, "split-tf32 stages come in the pair form or for single CTAs");
+    constexpr bool INT = KIND == KIND_I8;
+    constexpr bool SPLIT = KIND == KIND_TF32;
     constexpr int EPI_GROUPS = EG, EPI_THREADS = 128 * EG, EPI_COLS = BN / EG, LDG = 1;
-    constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;
+    constexpr int SB = stage_bytes_of(KIND, PAIR);
+    constexpr int XB = PAIR ? B_BYTES / 2 : B_BYTES;                    // bytes of one database-tile plane in this CTA
+    constexpr int X_OFF = planes_of(KIND) * A_BYTES;                    // database planes follow the query planes
+    constexpr int KELEMS = KIND == KIND_I8 ? 128 : (KIND == KIND_F16 ? 64 : 32);   // elements per 128-byte K block
     const uint32_t STAGES = p.stages;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve shared memory: operand ring (1024-byte aligned) | sort scratch | column params | barriers
@@ -299,6 +286,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_x);
+        if (SPLIT) { tma_prefetch_desc(&map_q2); tma_prefetch_desc(&map_x2); }
         for (uint32_t s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PAIR ? 1 : CL); }
         // pair form: the leader's MMA thread waits for the epilogue warps of BOTH CTAs before it overwrites an accumulator
         for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, (PAIR ? 2 : 1) * (EPI_THREADS / 32)); }
@@ -358,24 +346,35 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);          // every CTA of the cluster released the slot
                         TC_STAT_ADD(st_empty, c_e);
                         const uint32_t a_dst = smem_u32(ring + stage * SB);
-                        const int kc = (int)(kb * (INT ? 128u : 64u));   // element coordinate along K
+                        const int kc = (int)(kb * (uint32_t)KELEMS);     // element coordinate along K
                         if (PAIR) {
                             // both CTAs' bytes are counted on the leader's barrier, which alone expects them
                             if (crank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * SB);
                             tma_load_2d_pair(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
-                            tma_load_2d_pair(a_dst + A_BYTES, &map_x, full0 + 8 * stage, kc, (int)(t * BN + crank * (BN / 2)));
+                            tma_load_2d_pair(a_dst + X_OFF, &map_x, full0 + 8 * stage, kc, (int)(t * BN + crank * (BN / 2)));
+                            if (SPLIT) {
+                                tma_load_2d_pair(a_dst + A_BYTES, &map_q2, full0 + 8 * stage, kc, (int)(mt * BM));
+                                tma_load_2d_pair(a_dst + X_OFF + XB, &map_x2, full0 + 8 * stage, kc, (int)(t * BN + crank * (BN / 2)));
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             continue;
                         }
-                        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+                        mbar_expect_tx(full0 + 8 * stage, SB);
                         tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kc, (int)(mt * BM));
+                        if (SPLIT) {                                       // single-CTA split form: four plain tile loads
+                            tma_load_2d(a_dst + A_BYTES, &map_q2, full0 + 8 * stage, kc, (int)(mt * BM));
+                            tma_load_2d(a_dst + X_OFF, &map_x, full0 + 8 * stage, kc, (int)(t * BN));
+                            tma_load_2d(a_dst + X_OFF + XB, &map_x2, full0 + 8 * stage, kc, (int)(t * BN));
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         if (p.l2_prefetch_tiles && t + p.l2_prefetch_tiles < t1)   // pull a later tile's rows from HBM into L2 now
                             tma_prefetch_l2_2d(&map_x, kc, (int)((t + p.l2_prefetch_tiles) * BN + crank * (BN / CL)));
                         if (CL > 1)      // this CTA's share of the database tile, delivered to every CTA of the cluster
-                            tma_load_2d_mc(a_dst + A_BYTES + crank * (B_BYTES / CL), &map_x, full0 + 8 * stage, kc,
+                            tma_load_2d_mc(a_dst + X_OFF + crank * (B_BYTES / CL), &map_x, full0 + 8 * stage, kc,
                                            (int)(t * BN + crank * (BN / CL)), (uint16_t)((1u << CL) - 1));
                         else
-                            tma_load_2d(a_dst + A_BYTES, &map_x, full0 + 8 * stage, kc, (int)(t * BN));
+                            tma_load_2d(a_dst + X_OFF, &map_x, full0 + 8 * stage, kc, (int)(t * BN));
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -409,11 +408,21 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         TC_STAT_ADD(st_full, c_f);
                         tcgen05_fence_after();
                         const uint32_t a_addr = smem_u32(ring + stage * SB);
-                        const uint64_t adesc = make_sdesc(a_addr), bdesc = make_sdesc(a_addr + A_BYTES);
+                        const uint64_t adesc = make_sdesc(a_addr), bdesc = make_sdesc(a_addr + X_OFF);
+                        [[maybe_unused]] const uint64_t adesc_lo = make_sdesc(a_addr + A_BYTES), bdesc_lo = make_sdesc(a_addr + X_OFF + XB);
 #pragma unroll
                         for (uint32_t ks = 0; ks < 4; ks++) {            // 4 x 32 bytes of K per 128-byte block
-                            if (PAIR) umma_pair<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
-                            else umma<INT>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                            if (PAIR) umma_pair<KIND>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                            else umma<KIND>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                            if (SPLIT) {                                 // the two cross terms of the split product
+                                if (PAIR) {
+                                    umma_pair<KIND>(d_tmem, adesc_lo + 2 * ks, bdesc + 2 * ks, p.idesc, 1u);
+                                    umma_pair<KIND>(d_tmem, adesc + 2 * ks, bdesc_lo + 2 * ks, p.idesc, 1u);
+                                } else {
+                                    umma<KIND>(d_tmem, adesc_lo + 2 * ks, bdesc + 2 * ks, p.idesc, 1u);
+                                    umma<KIND>(d_tmem, adesc + 2 * ks, bdesc_lo + 2 * ks, p.idesc, 1u);
+                                }
+                            }
                         }
                         if (PAIR) umma_commit_pair(empty0 + 8 * stage, 3);
                         else if (CL > 1) umma_commit_mc(empty0 + 8 * stage, (uint16_t)((1u << CL) - 1));   // slot free in every CTA
@@ -722,6 +731,64 @@ __global__ void __launch_bounds__(128) prep_queries(const void* q, unsigned char
         qconst[qi] = c;
     }
 }
+
+// ---- K2' (Float32 spaces): the two tf32-exact planes of an operand ------------------------------------------
+// hi = tf32(x) (round to nearest, low 13 mantissa bits zero), lo = tf32(x - hi); x - hi is exact in f32, so
+// x = hi + lo + O(2^-22 |x|) and both planes pass through the tensor core's tf32 inputs unchanged whatever
+// rounding it applies to wider values.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u & 0xffffe000u);
+}
+__device__ __forceinline__ void tf32_split(float x, float* hi, float* lo) {
+    const float h = tf32_rn(x);
+    *hi = h; *lo = tf32_rn(x - h);
+}
+#ifdef MVF_TC_PATH_TU   // non-template kernels: defined in tc_path.cu's translation unit only
+// rows of an f32 shard -> [hi plane | lo plane], same pitch; one thread per 16-byte chunk
+__global__ void __launch_bounds__(256) split_rows_tf32_kernel(const unsigned char* rows, uint64_t nbytes, unsigned char* out) {
+    const uint64_t chunks = nbytes >> 4;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = k::ldg_stream16(rows + c * 16);
+        const float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) tf32_split(x[e], &h[e], &l[e]);
+        *reinterpret_cast<float4*>(out + c * 16) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(out + nbytes + c * 16) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+// query preparation for the split form: planes hi (out) and lo (out + plane_bytes), per-query constant from the f32 values
+__global__ void __launch_bounds__(128) prep_queries_tf32(const float* q, unsigned char* out, size_t plane_bytes, uint32_t nq, uint32_t d,
+                                                         uint32_t pitch, float* qconst, int metric) {
+    const uint32_t qi = blockIdx.x;
+    if (qi >= nq) return;
+    const float* src = q + (size_t)qi * d;
+    float* dh = reinterpret_cast<float*>(out + (size_t)qi * pitch);
+    float* dl = reinterpret_cast<float*>(out + plane_bytes + (size_t)qi * pitch);
+    float fs = 0.f;
+    for (uint32_t j = threadIdx.x; j < pitch / 4; j += blockDim.x) {
+        const float v = j < d ? src[j] : 0.f;
+        float h, l;
+        tf32_split(v, &h, &l);
+        dh[j] = h; dl[j] = l;
+        fs = fmaf(v, v, fs);
+    }
+    __shared__ float rf[4];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, off);
+    if ((threadIdx.x & 31) == 0) rf[threadIdx.x >> 5] = fs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float f = rf[0] + rf[1] + rf[2] + rf[3];
+        float c;
+        if (metric == k::M_COS) { const float nm = sqrtf(f); c = nm > 0.f ? 1.0f / nm : 0.0f; }
+        else c = f;
+        qconst[qi] = c;
+    }
+}
+#endif  // MVF_TC_PATH_TU
 
 }  // namespace tc
 }  // namespace mvf

@@ -37,7 +37,12 @@ def main():
     cases = [(0, 0, 20000, 128, 10, 3), (1, 2, 30001, 96, 10, 2), (3, 0, 50000, 128, 25, 4), (2, 1, 7, 16, 5, 2),
              (3, 2, 40000, 64, 10, 1), (0, 1, 1000, 768, 100, 9),
              # batches that take the tensor-core path on every rank (keys are K2 ranking values until the final merge)
-             (3, 0, 60000, 128, 10, 40), (1, 2, 50000, 128, 10, 70), (1, 0, 50000, 64, 33, 130), (2, 1, 40000, 96, 10, 16)]
+             (3, 0, 60000, 128, 10, 40), (1, 2, 50000, 128, 10, 70), (1, 0, 50000, 64, 33, 130), (2, 1, 40000, 96, 10, 16),
+             # Float32 batches: the split-tf32 form (K2')
+             (0, 0, 60000, 96, 10, 48), (0, 2, 50000, 128, 10, 200),
+             # the tail shard falls under the tensor path's minimum (4096 rows) while the others do not: every rank must
+             # make the same choice or the exchanged keys are in two encodings
+             (1, 2, world * 4096 - 1, 64, 10, 8), (3, 0, world * 4096 - 1, 128, 10, 16)]
     for dtype, metric, n, d, k, nq in cases:
         gs = eng.synthetic(mv.DataType(dtype), mv.DistanceMetric(metric), n, d, seed=321)
         b, c = mv.shard_range(n, world, rank)
@@ -54,13 +59,61 @@ def main():
             db = mv.synth_fill_host(dtype, 321, 0, n, d)
             check_batch(db, dtype, metric, queries.astype(np.float32) if dtype == 1 else queries, k, ids, sc, isc)
             full = solo.from_host(db, mv.DataType(dtype), mv.DistanceMetric(metric))
+            # tail-shard cases: the sharded ranks stay on the scan kernel (4095-row tail); compare like with like
+            solo.set_path(1 if n == world * 4096 - 1 else 0)
             ids1, sc1, isc1 = full.search(queries, k)
+            solo.set_path(0)
             same = np.array_equal(ids, ids1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32)) and np.array_equal(isc, isc1)
             if not same:
                 failures += 1
                 print("MISMATCH sharded vs single", (dtype, metric, n, d, k, nq))
             full.free()
         gs.free()
+    # forced tensor path with empty tail shards (fewer rows than ranks)
+    eng.set_path(2)
+    if solo is not None:
+        solo.set_path(2)
+    for dtype, n, d, nq in ((3, 1, 128, 9), (1, max(1, world - 1), 64, 5)):
+        gs = eng.synthetic(mv.DataType(dtype), mv.DistanceMetric.L2, n, d, seed=11)
+        q = mv.synth_fill_host(dtype, 12, 0, nq, d)
+        ids, sc, isc = gs.search(q, 4)
+        if rank == 0:
+            db = mv.synth_fill_host(dtype, 11, 0, n, d)
+            full = solo.from_host(db, mv.DataType(dtype), mv.DistanceMetric.L2)
+            ids1, sc1, isc1 = full.search(q, 4)
+            if not (np.array_equal(ids, ids1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32))):
+                failures += 1
+                print("MISMATCH forced tensor path with empty shards", (dtype, n))
+            full.free()
+        gs.free()
+    eng.set_path(0)
+    if solo is not None:
+        solo.set_path(0)
+    # block checksum of a sharded upload: every rank hashes its rows, the shard CRCs are combined (collective call)
+    import tempfile
+    import zlib
+    n, d = 20000, 40
+    dbf = mv.synth_fill_host(1, 91, 0, n, d)
+    path = os.path.join(tempfile.gettempdir(), "mvf_multirank_%d.mvf" % os.getppid())
+    if local == 0:
+        b = mv.MvfBuilder()
+        b.add_vector_space("s", d, mv.VectorType.Dense, mv.DistanceMetric.Cosine, mv.DataType.Float16)
+        b.add_vectors_raw("s", dbf)
+        b.save(path)
+    dist.barrier()
+    r = mv.MvfReader.open(path)
+    sp = r.vector_space("s")
+    gs = eng.upload(sp)
+    crc, _ = gs.checksum()
+    gs.verify_checksum(sp)
+    if crc != (zlib.crc32(dbf.tobytes()) & 0xffffffff):
+        failures += 1
+        print("MISMATCH sharded checksum on rank", rank)
+    gs.free()
+    r.close()
+    dist.barrier()
+    if local == 0:
+        os.remove(path)
     # external ids and a global row mask on a sharded space: ids table replicated, mask re-based per shard
     n, d, k = 30000, 64, 10
     gs = eng.synthetic(mv.DataType.UInt8, mv.DistanceMetric.L2, n, d, seed=77)

@@ -14,7 +14,7 @@ import pytest
 
 import metrovector_b200 as mv
 import oracle
-from util import as_query
+from util import as_query, ids_agree_within_tolerance
 
 pytestmark = pytest.mark.gpu
 SEED = 0x4D564631
@@ -96,3 +96,50 @@ def test_shard_additivity_at_size(engine, n, d, dtype, metric):
         merged = sorted(cand.items(), key=lambda kv: (kv[1][0], kv[0]))[:k]
         assert [m[0] for m in merged] == w_ids[qi].tolist()
         assert [m[1][0] for m in merged] == [float(x) for x in w_sc[qi]]
+
+
+# ---- the batched (tensor-core) path at BASELINE.json's full sizes ---------------------------------------------------
+@pytest.mark.parametrize("name,n,d,dtype,metric,k,nq", [
+    ("C", 10_000_000, 768, oracle.F16, oracle.COS, 100, 4096),          # BASELINE configs[2], full size
+    ("D1024-slab", 12_500_000, 768, oracle.F16, oracle.COS, 10, 1024),  # one 8-GPU shard of configs[3], batch 1024
+    ("E1024-slab", 125_000_000, 128, oracle.U8, oracle.L2, 10, 1024),   # one 8-GPU shard of configs[4], batch 1024
+    ("B1024", 1_000_000, 768, oracle.F32, oracle.L2, 10, 1024),         # configs[1]'s space, batch 1024 (split tf32)
+])
+def test_full_size_tensor_path(engine, name, n, d, dtype, metric, k, nq):
+    gs = engine.synthetic(mv.DataType(dtype), mv.DistanceMetric(metric), n, d, SEED)
+    q = mv.synth_fill_host(dtype, SEED + 1, 0, nq, d)
+    planted = {0: 0, 1: n // 3, 127: n // 2, nq - 128: 12345, nq - 1: n - 1}   # query slot -> stored row, first and last query tile
+    for slot, r in planted.items():
+        q[slot] = mv.synth_fill_host(dtype, SEED, r, 1, d)[0]
+    try:
+        engine.set_path(0)
+        ids, sc, isc = gs.search(q, k)
+        assert engine.profile_read()["last_path"] == 2, "the batch did not take the tensor-core path"
+        for slot, r in planted.items():
+            assert ids[slot][0] == r, (name, slot, r, ids[slot])
+            if metric != oracle.L2:
+                assert abs(sc[slot][0]) <= 2e-5
+            elif dtype in (oracle.I8, oracle.U8):
+                assert sc[slot][0] == 0.0 and isc[slot][0] == 0
+            else:       # |q|^2 + |x|^2 - 2 q.x cancels to within the stated tolerance on d^2, not to an exact zero
+                qn2 = float(np.dot(q[slot].astype(np.float64), q[slot].astype(np.float64)))
+                assert float(sc[slot][0]) ** 2 <= 1e-5 * 2 * qn2, (name, slot, sc[slot][0])
+        assert all(len(set(ids[i].tolist())) == k and ids[i].max() < n for i in range(nq))
+        # every query of the first and of the last 128-query tile again through the bandwidth scan (itself checked
+        # against the oracle at these sizes above): bit-identical for integers, the id rule for floats
+        engine.set_path(1)
+        for lo in (0, nq - 128):
+            a = gs.search(q[lo:lo + 128], k)
+            assert engine.profile_read()["last_path"] == 1
+            if dtype in (oracle.I8, oracle.U8):
+                assert np.array_equal(a[0], ids[lo:lo + 128]) and np.array_equal(a[2], isc[lo:lo + 128]), (name, lo)
+            else:
+                assert np.allclose(a[1], sc[lo:lo + 128], rtol=1e-4, atol=2e-5), (name, lo)
+                assert ids_agree_within_tolerance(metric, a[0], a[1], ids[lo:lo + 128], sc[lo:lo + 128]), (name, lo)
+        # and the oracle's own score for every returned row of a few queries
+        for i in (2, 64, nq - 2):
+            qq = q[i].astype(np.float32) if dtype in (oracle.F32, oracle.F16) else q[i]
+            _check_consistency(dtype, metric, d, qq, ids[i], sc[i], isc[i])
+    finally:
+        engine.set_path(0)
+        gs.free()

@@ -4,10 +4,11 @@ import pytest
 
 import metrovector_b200 as mv
 import oracle
-from util import check_batch
+from util import check_batch, ids_agree_within_tolerance
 
 pytestmark = pytest.mark.gpu
-DT = {oracle.F16: mv.DataType.Float16, oracle.I8: mv.DataType.Int8, oracle.U8: mv.DataType.UInt8}
+DT = {oracle.F32: mv.DataType.Float32, oracle.F16: mv.DataType.Float16, oracle.I8: mv.DataType.Int8, oracle.U8: mv.DataType.UInt8}
+FLOATS = (oracle.F32, oracle.F16)       # Float32 spaces run the split-tf32 form (K2'), Float16 ones kind::f16
 
 
 def _rank_values(db, q, dtype, metric):
@@ -24,38 +25,45 @@ def _rank_values(db, q, dtype, metric):
 
 
 @pytest.mark.parametrize("dtype,d", [(oracle.F16, 64), (oracle.F16, 768), (oracle.F16, 200), (oracle.U8, 128), (oracle.I8, 96),
-                                     (oracle.U8, 300)])
+                                     (oracle.U8, 300), (oracle.F32, 32), (oracle.F32, 768), (oracle.F32, 100)])
 def test_raw_contraction_matches_numpy(engine, dtype, d):
     n, nq = 700, 130                       # 3 database tiles (last one partial), 2 query tiles (last one partial)
     db = mv.synth_fill_host(dtype, 31, 0, n, d)
     q = mv.synth_fill_host(dtype, 32, 0, nq, d)
     gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
-    metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)
+    metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
     for metric in metrics:
         got = gs.tc_dump(q, k=10, metric=metric)[:nq, :n]
         want = _rank_values(db, q, dtype, metric)
-        if dtype == oracle.F16:
+        if dtype in FLOATS:
             scale = np.abs(want).max()
+            # f16 products are exact in f32; the split-tf32 product drops a 2^-22 term: both far inside 1e-5 of the scale
             assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * scale), (metric, np.abs(got - want).max())
+            if dtype == oracle.F32:
+                assert np.abs(got - want).max() <= 2e-6 * scale, (metric, np.abs(got - want).max() / scale)
         else:
             assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), metric
     gs.free()
 
 
 @pytest.mark.parametrize("dtype,d,n", [(oracle.F16, 128, 20000), (oracle.F16, 768, 9000), (oracle.U8, 128, 30000),
-                                       (oracle.I8, 64, 12345), (oracle.F16, 72, 5000)])
+                                       (oracle.I8, 64, 12345), (oracle.F16, 72, 5000), (oracle.F32, 128, 20000),
+                                       (oracle.F32, 768, 6000), (oracle.F32, 72, 5000)])
 def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
     db = mv.synth_fill_host(dtype, 41, 0, n, d)
     gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
     engine.set_path(2)
     try:
-        metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)
+        metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
         for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33), (130, 128)):
             q = mv.synth_fill_host(dtype, 42, 0, nq, d)
             q[0] = db[n // 2]
+            # one query tile of a Float32 space with k > 56 has no split-tf32 launch shape (96 KiB stages beside a
+            # 512-entry sort scratch): that combination stays on the scan kernel by design
+            want_path = 1 if (dtype == oracle.F32 and nq <= 128 and k > 56) else 2
             for metric in metrics:
                 ids, sc, isc = gs.search(q, k, metric=metric)
-                assert engine.profile_read()["last_path"] == 2
+                assert engine.profile_read()["last_path"] == want_path
                 qq = q.astype(np.float32) if dtype == oracle.F16 else q
                 check_batch(db, dtype, metric, qq[:16], k, ids[:16], sc[:16], isc[:16])
                 check_batch(db, dtype, metric, qq[-3:], k, ids[-3:], sc[-3:], isc[-3:])
@@ -65,7 +73,8 @@ def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
 
 
 @pytest.mark.parametrize("dtype,n,d,nq,k", [(oracle.U8, 50000, 256, 96, 10), (oracle.U8, 3_000_000, 128, 200, 10),
-                                            (oracle.I8, 2_000_000, 96, 130, 33), (oracle.F16, 1_000_000, 128, 130, 10)])
+                                            (oracle.I8, 2_000_000, 96, 130, 33), (oracle.F16, 1_000_000, 128, 130, 10),
+                                            (oracle.F32, 1_000_000, 128, 130, 10), (oracle.F32, 400_000, 768, 300, 100)])
 def test_tensor_and_scan_paths_agree(engine, dtype, n, d, nq, k):
     # sizes beyond the CPU oracle: the two GPU paths (each checked against the oracle at small sizes) must agree
     # on every metric.  Many database tiles per CTA exercise the threshold / early-out logic of the K2 epilogue.
@@ -73,15 +82,15 @@ def test_tensor_and_scan_paths_agree(engine, dtype, n, d, nq, k):
     q = mv.synth_fill_host(dtype, 52, 0, nq, d)
     try:
         # integer cosine stays on the scan path by design (exact definition needs a division per element)
-        for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)):
+        for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)):
             engine.set_path(1)
             a = gs.search(q, k, metric=metric)
             engine.set_path(2)
             b = gs.search(q, k, metric=metric)
             assert engine.profile_read()["last_path"] == 2
-            if dtype == oracle.F16:                                          # accumulation order differs
+            if dtype in FLOATS:                                              # accumulation order differs
                 assert np.allclose(a[1], b[1], rtol=1e-4, atol=1e-5), metric
-                assert (a[0] == b[0]).mean() > 0.98, metric
+                assert ids_agree_within_tolerance(metric, a[0], a[1], b[0], b[1]), metric
             else:                                                            # integers: bit-identical
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]), metric
     finally:
@@ -126,11 +135,11 @@ def test_every_kernel_form_matches_oracle(env, monkeypatch):
     eng = mv.GpuEngine(0)
     eng.set_path(2)
     try:
-        for dtype, d, n in ((oracle.U8, 128, 40000), (oracle.I8, 320, 9000), (oracle.F16, 96, 30000)):
+        for dtype, d, n in ((oracle.U8, 128, 40000), (oracle.I8, 320, 9000), (oracle.F16, 96, 30000), (oracle.F32, 96, 30000)):
             db = mv.synth_fill_host(dtype, 61, 0, n, d)
             gs = eng.from_host(db, DT[dtype], mv.DistanceMetric.L2)
             q = mv.synth_fill_host(dtype, 62, 0, 300, d)
-            for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype == oracle.F16 else (oracle.L2, oracle.IP)):
+            for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)):
                 ids, sc, isc = gs.search(q, 10, metric=metric)
                 assert eng.profile_read()["last_path"] == 2
                 qq = q.astype(np.float32) if dtype == oracle.F16 else q

@@ -342,6 +342,31 @@ def test_vector_ids_tombstone_list_and_metadata_column_round_trip(tmp_path):
     assert parsed["spaces"][0]["vector_ids_block_index"] == 4 and parsed["spaces"][1]["vector_ids_block_index"] == 0
 
 
+def test_side_tables_are_rechecked_against_the_rows_at_save_time(tmp_path):
+    # ids / tombstones were only validated when they were set; rows added afterwards produced a file every reader
+    # (ours included) rejects as CorruptedData
+    rows = np.arange(12 * 4, dtype=np.float32).reshape(12, 4)
+    b = mv.MvfBuilder()
+    b.add_vector_space("a", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    b.add_vectors("a", rows[:8])
+    b.set_vector_ids("a", np.arange(8, dtype=np.uint64))
+    b.add_vectors("a", rows[8:])                                # 12 rows now, 8 ids
+    with pytest.raises(mv.DimensionMismatch):
+        b.save(str(tmp_path / "bad.mvf"))
+    b.set_vector_ids("a", np.arange(12, dtype=np.uint64))
+    b.save(str(tmp_path / "good.mvf"))
+    assert mv.MvfReader.open(str(tmp_path / "good.mvf")).vector_space("a").vector_ids().tolist() == list(range(12))
+    c = mv.MvfBuilder()
+    c.add_vector_space("a", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    c.add_vectors("a", rows[:8])
+    c.set_tombstones("a", np.zeros(8, dtype=bool))
+    c.add_vectors("a", rows)                                    # 20 rows, an 8-bit bitmap
+    with pytest.raises(mv.DimensionMismatch):
+        c.save(str(tmp_path / "bad2.mvf"))
+    with pytest.raises(mv.Io):
+        b.save(str(tmp_path / "no_such_dir" / "x.mvf"))
+
+
 @pytest.mark.parametrize("dt,np_dt", [(mv.DataType.UInt8, np.uint8), (mv.DataType.Int8, np.int8), (mv.DataType.UInt32, np.uint32),
                                       (mv.DataType.UInt64, np.uint64), (mv.DataType.Float16, np.float16)])
 def test_filter_range_bitmap_every_dtype(dt, np_dt):
@@ -451,3 +476,21 @@ def test_random_files_round_trip_and_match_the_independent_writer(tmp_path):
             assert (s.tombstones() is None) == ("tombstones" not in d)
         for c in cols:
             assert r.metadata_column(c["name"])[0] == c["data"]
+
+
+def test_structured_error_fields_cross_the_abi(golden_dir):
+    # IndexOutOfBounds{index, len} / DimensionMismatch{expected, actual} (src/errors.rs:21-25) keep their numbers
+    # through the C ABI (mvf_last_error_fields), so a binding rebuilds the exact variant
+    r = mv.MvfReader.open(os.path.join(golden_dir, "simple_f32.mvf"))
+    sp = r.vector_space("embeddings")
+    with pytest.raises(mv.IndexOutOfBounds) as ei:
+        sp.get_vector(999)                                        # src/vectors/vector_space.rs:385-397
+    assert ei.value.fields == (999, sp.total_vectors())
+    with pytest.raises(mv.VectorSpaceNotFound) as ei:
+        r.vector_space("nope")
+    assert ei.value.fields == (0, 0)
+    b = mv.MvfBuilder()
+    b.add_vector_space("a", 4, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
+    with pytest.raises(mv.DimensionMismatch) as ei:
+        b.add_vectors("a", np.zeros((2, 5), dtype=np.float32))
+    assert ei.value.fields == (4, 5)

@@ -88,3 +88,23 @@ def check_one(db, dtype, metric, query, k, ids, scores, iscores):
 def check_batch(db, dtype, metric, queries, k, ids, scores, iscores):
     for qi in range(len(queries)):
         check_one(db, dtype, metric, queries[qi], k, ids[qi], scores[qi], iscores[qi])
+
+
+def ids_agree_within_tolerance(metric, ids_a, sc_a, ids_b, sc_b):
+    """Two float result sets of the same queries (e.g. scan kernel vs tensor kernel, whose summation orders differ):
+    the id rule of SURVEY.md section 8a without an oracle -- every id one side ranks clearly inside its top-k (better
+    than BOTH k-th scores by more than twice the tolerance) must be in the other side's list.  Positions may differ
+    only among scores closer than that."""
+    for q in range(ids_a.shape[0]):
+        if np.array_equal(ids_a[q], ids_b[q]):
+            continue
+        ra = np.array([_rank_value(metric, s, False) for s in sc_a[q]])
+        rb = np.array([_rank_value(metric, s, False) for s in sc_b[q]])
+        scale = max(1.0, float(np.abs(ra).max()), float(np.abs(rb).max()))
+        tol = (TOL_COS_ABS if metric == oracle.COS else 1e-5) * scale
+        kth = min(ra[-1], rb[-1])
+        clear_a = set(int(i) for i, r in zip(ids_a[q], ra) if r < kth - 2 * tol)
+        clear_b = set(int(i) for i, r in zip(ids_b[q], rb) if r < kth - 2 * tol)
+        if not clear_a.issubset(set(int(i) for i in ids_b[q])) or not clear_b.issubset(set(int(i) for i in ids_a[q])):
+            return False
+    return True
