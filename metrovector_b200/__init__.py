@@ -15,7 +15,8 @@ from collections import namedtuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvf_b200.so")
+# MVF_B200_LIB selects another build of the same library (e.g. the -DMVF_TC_STATS diagnostic build, scripts/gpu_stats.sh)
+LIB_PATH = os.environ.get("MVF_B200_LIB") or os.path.join(_HERE, "libmvf_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

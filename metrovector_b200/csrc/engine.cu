@@ -122,7 +122,7 @@ struct mvf_gpu {
     std::vector<unsigned char*> stage_pool;   // pinned staging buffers (16 MiB each), kept across uploads
     int upload_threads = 8;                // MVF_UPLOAD_THREADS
     std::map<std::pair<const void*, size_t>, int> occ_cache;
-    std::set<const void*> smem_optin_set;   // kernels whose dynamic shared-memory limit was raised on THIS device
+    std::map<const void*, size_t> smem_optin_max;   // dynamic shared-memory limit raised so far per kernel, on THIS device
     uint32_t* pinned_flag = nullptr;       // mapped pinned word the device writes "this query batch holds Inf/NaN" into
     uint32_t* pinned_flag_dev = nullptr;
     cudaEvent_t xdev_event = nullptr;      // group engines: orders a member's stream against another member's
@@ -186,17 +186,19 @@ struct ScanTimer {   // brackets the dominant kernel with events when profiling 
 };
 
 // the dynamic shared-memory opt-in is a per-device function attribute: remembered per engine, not per process
+// and only ever raised (a later, smaller request must not lower the limit under a launch shape cached earlier).
 void allow_smem(mvf_gpu* g, const void* fn, size_t bytes) {
-    if (g->smem_optin_set.count(fn)) return;
+    size_t& have = g->smem_optin_max[fn];
+    if (bytes <= have) return;
     CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    g->smem_optin_set.insert(fn);
+    have = bytes;
 }
 
 int occupancy(mvf_gpu* g, const void* fn, int threads, size_t smem) {
     auto key = std::make_pair(fn, smem);
     auto it = g->occ_cache.find(key);
     if (it != g->occ_cache.end()) return it->second;
-    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) allow_smem(g, fn, smem);
     int nb = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem));
     if (nb < 1) throw MvfError::cuda("kernel does not fit on an SM (shared memory " + std::to_string(smem) + " B)");

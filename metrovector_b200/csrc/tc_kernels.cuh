@@ -192,6 +192,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+          "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+          "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 128 bytes, 8-row groups
 // 1024 bytes apart): start>>4 | LBO=1 | SBO=64 | version=1 | layout SWIZZLE_128B
@@ -256,6 +292,9 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // a stage holds [Q_hi | Q_lo | X_hi | X_lo] and every K step issues three MMAs (hi.hi, lo.hi, hi.lo), so the
 // accumulator carries q.x to ~2^-21 relative (the dropped lo.lo term) -- inside the float tolerance of the scan.
 template <int KIND, int MODE, int CL, int EG, bool PAIR>
+// (64 + 128 * EG threads, one CTA per SM.  With four epilogue warpgroups that is 18 warps, five on two of the four SM
+// sub-partitions, whose 16K-register files then cap a thread at 102 registers: ptxas stops at 96 and a __maxnreg__ of
+// 104 is refused at launch -- measured.)
 __global__ void __launch_bounds__(threads_for(EG), 1)
 gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
              const __grid_constant__ CUtensorMap map_q2, const __grid_constant__ CUtensorMap map_x2, const TcParams p) {
@@ -263,7 +302,16 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     static_assert(KIND != KIND_TF32 || PAIR || CL == 1, "split-tf32 stages come in the pair form or for single CTAs");
     constexpr bool INT = KIND == KIND_I8;
     constexpr bool SPLIT = KIND == KIND_TF32;
+    // Integer L2 ("accumulator-init" form): the epilogue warps pre-load every accumulator column with -(|x|^2 >> 1)
+    // (tcgen05.st, two tiles ahead) and the MMAs accumulate on top of it, so a tile comes out of TMEM as
+    // r = q.x - (|x|^2 >> 1) and the ranking value is s = |x|^2 - 2 q.x = (|x|^2 & 1) - 2r: the common path is a
+    // max tree over r (one VIMNMX3 per two elements, like the dot-product metric) against the conservative bound
+    // r >= -(thr >> 1); the exact s (with the parity bit) is only formed for the rare candidates.  The per-element
+    // IADD3 (|x|^2 - 2a) and the parameter LDS of the old form were 2/3 of the epilogue's instructions on short
+    // rows (config E batched: 512 MMA cycles per tile against ~2300 measured).
+    constexpr bool INIT_ACC = INT && MODE == 0;
     constexpr int EPI_GROUPS = EG, EPI_THREADS = 128 * EG, EPI_COLS = BN / EG, LDG = 1;
+    constexpr int PSLOTS = 3;                                           // column-parameter slots per epilogue warp (tc_path.hpp smem_bytes)
     constexpr int SB = stage_bytes_of(KIND, PAIR);
     constexpr int XB = PAIR ? B_BYTES / 2 : B_BYTES;                    // bytes of one database-tile plane in this CTA
     constexpr int X_OFF = planes_of(KIND) * A_BYTES;                    // database planes follow the query planes
@@ -274,10 +322,11 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = smem;
     u64* scratch = reinterpret_cast<u64*>(ring + STAGES * SB);           // [epilogue warps][cap]
-    float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [epilogue warps][2][EPI_COLS], warp-private
-    uint64_t* bars = reinterpret_cast<uint64_t*>(prm + (EPI_THREADS / 32) * 2 * EPI_COLS);   // full[S] empty[S] tfull[2] tempty[2]
+    float* prm = reinterpret_cast<float*>(scratch + (EPI_THREADS / 32) * p.cap);  // [epilogue warps][PSLOTS][EPI_COLS], warp-private
+    uint64_t* bars = reinterpret_cast<uint64_t*>(prm + (EPI_THREADS / 32) * PSLOTS * EPI_COLS);   // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
-    uint32_t* valid_s = tmem_slot + 4;                                                    // [epilogue warps][2][EPI_COLS / 32] live-column words
+    uint32_t* valid_s = tmem_slot + 4;                                                    // [epilogue warps][PSLOTS][EPI_COLS / 32] live-column words
+    uint32_t* odd_s = valid_s + (EPI_THREADS / 32) * PSLOTS * (EPI_COLS / 32);            // same shape: parity of |x|^2 per column (INIT_ACC)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES);
@@ -397,8 +446,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 const uint32_t t1 = min(t0 + p.tiles_per_chunk, p.ntiles);
                 for (uint32_t t = t0; t < t1; t++) {
                     TC_STAT_BEGIN(c_t);
-                    if (PAIR) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
-                    else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+                    // INIT_ACC: the epilogue also arrives once per accumulator up front (after seeding it), so there is
+                    // no free first pass
+                    if (PAIR) mbar_wait_cluster(tempty0 + 8 * acc, INIT_ACC ? acc_phase : acc_phase ^ 1);   // both CTAs' epilogues have drained it
+                    else mbar_wait(tempty0 + 8 * acc, INIT_ACC ? acc_phase : acc_phase ^ 1);      // epilogue has drained (and re-seeded) this accumulator
                     TC_STAT_ADD(st_tempty, c_t);
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
@@ -412,8 +463,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         [[maybe_unused]] const uint64_t adesc_lo = make_sdesc(a_addr + A_BYTES), bdesc_lo = make_sdesc(a_addr + X_OFF + XB);
 #pragma unroll
                         for (uint32_t ks = 0; ks < 4; ks++) {            // 4 x 32 bytes of K per 128-byte block
-                            if (PAIR) umma_pair<KIND>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
-                            else umma<KIND>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, (kb | ks) != 0);
+                            if (PAIR) umma_pair<KIND>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, INIT_ACC || (kb | ks) != 0);
+                            else umma<KIND>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, p.idesc, INIT_ACC || (kb | ks) != 0);
                             if (SPLIT) {                                 // the two cross terms of the split product
                                 if (PAIR) {
                                     umma_pair<KIND>(d_tmem, adesc_lo + 2 * ks, bdesc + 2 * ks, p.idesc, 1u);
@@ -440,26 +491,30 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #endif
         }
     } else {
-        // ===== epilogue: 2 warpgroups x 4 warps; a thread owns one query (TMEM lane) and the
-        // warpgroup's half of the tile's columns =====
+        // ===== epilogue: EG warpgroups x 4 warps; a thread owns one query (TMEM lane) and the
+        // warpgroup's slice of the tile's columns =====
         const int quarter = warp & 3;                                   // TMEM lanes 32*quarter .. +31
-        const int grp = (warp - 2) >> 2;                                // column half
+        const int grp = (warp - 2) >> 2;                                // column slice
         const int qrow = quarter * 32 + lane;                           // query row inside the tile
         u64* wscratch = scratch + (size_t)(warp - 2) * p.cap;
         u64* const cta_cand = p.cand + ((size_t)blockIdx.x * EPI_GROUPS + grp) * BM * p.cap;
         u64* mybuf = cta_cand + (size_t)qrow * p.cap;
         // Per-column parameter of the ranking value and whether the column is a live row (inside the database,
-        // not deleted / filtered out).  Every epilogue warp stages the EPI_COLS columns of ITS half in a private
-        // shared-memory slice, one tile ahead (4 columns per lane), so the epilogue needs no CTA-wide barrier.
+        // not deleted / filtered out).  Every epilogue warp stages the EPI_COLS columns of ITS slice in a private
+        // shared-memory slice ahead of time (EPI_COLS / 32 columns per lane), so the epilogue needs no CTA-wide
+        // barrier.  PSLOTS slots: float kinds work one tile ahead (slot = accumulator), integer kinds three.
         constexpr int CPLANE = EPI_COLS / 32;
-        float* my_prm = prm + (size_t)(warp - 2) * 2 * EPI_COLS;
-        uint32_t* my_valid = valid_s + (warp - 2) * 2 * CPLANE;
-        // Split in two so the global loads of tile t+1 are ISSUED before tile t is processed and only CONSUMED after
-        // it (their ~1 us latency used to sit in front of every tile's accumulator wait): load_raw returns the
-        // untouched words, finish_param turns them into (parameter, live).
+        float* my_prm = prm + (size_t)(warp - 2) * PSLOTS * EPI_COLS;
+        uint32_t* my_valid = valid_s + (warp - 2) * PSLOTS * CPLANE;
+        uint32_t* my_odd = odd_s + (warp - 2) * PSLOTS * CPLANE;
+        // Split in two so the global loads of a later tile are ISSUED before the current tile is processed and only
+        // CONSUMED after it (their ~1 us latency used to sit in front of every tile's accumulator wait): load_raw
+        // returns the untouched words, finish_param turns them into (parameter, live).
+        const uint32_t n32 = (uint32_t)p.n;                             // a resident shard holds < 2^32 rows
+        const uint32_t col0 = (uint32_t)(grp * EPI_COLS + lane);
         auto load_raw = [&](uint32_t t, int j, float* raw, uint32_t* mword) {
-            const uint64_t row = (uint64_t)t * BN + grp * EPI_COLS + j * 32 + lane;
-            const bool in = row < p.n;
+            const uint32_t row = t * BN + col0 + j * 32;                  // (the padded tile range stays below 2^32 + BN: wraps only past n)
+            const bool in = row < n32 && row >= t * BN;
             *mword = (in && p.mask != nullptr) ? p.mask[row >> 5] : 0u;
             float v = 0.f;
             if (in) {
@@ -469,22 +524,99 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             *raw = v;
         };
         auto finish_param = [&](uint32_t t, int j, float raw, uint32_t mword, bool* live) -> float {
-            const uint64_t row = (uint64_t)t * BN + grp * EPI_COLS + j * 32 + lane;
-            const bool ok = row < p.n && ((mword >> (row & 31)) & 1u) == 0;
+            const uint32_t row = t * BN + col0 + j * 32;
+            const bool ok = row < n32 && row >= t * BN && ((mword >> (row & 31)) & 1u) == 0;
             *live = ok;
             if (!ok) return __int_as_float(0);
+            if (INIT_ACC) return __int_as_float(-(__float_as_int(raw) >> 1));     // the accumulator seed; the parity goes to odd_s
             if (MODE == 0) return raw;
             if (INT) return __int_as_float(0);
             if (p.metric == k::M_COS) return raw > 0.f ? -1.0f / raw : 0.0f;
             return -1.0f;
         };
-        auto load_param = [&](uint32_t t, int j, bool* live) -> float {
-            float raw; uint32_t mw;
-            load_raw(t, j, &raw, &mw);
-            return finish_param(t, j, raw, mw, live);
+        // publishes the parameters of database tile t in slot `slot` of the warp's private slice (from raw words loaded earlier)
+        auto publish_params = [&](uint32_t slot, uint32_t t, const float* raw, const uint32_t* mw) {
+            float* prn = my_prm + slot * EPI_COLS;
+#pragma unroll
+            for (int j = 0; j < CPLANE; j++) {
+                bool lv;
+                prn[j * 32 + lane] = finish_param(t, j, raw[j], mw[j], &lv);
+                const unsigned vw = __ballot_sync(0xffffffffu, lv);
+                if (lane == 0) my_valid[slot * CPLANE + j] = vw;
+                if (INIT_ACC) {
+                    const unsigned ow = __ballot_sync(0xffffffffu, (__float_as_int(raw[j]) & 1) != 0);
+                    if (lane == 0) my_odd[slot * CPLANE + j] = ow;
+                }
+            }
+        };
+        // INIT_ACC: seeds accumulator `a` (this warp's lane quarter and column slice) with the values published in `slot`
+        [[maybe_unused]] auto seed_accumulator = [&](uint32_t a, uint32_t slot) {
+            const uint4* pi = reinterpret_cast<const uint4*>(my_prm + slot * EPI_COLS);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + grp * EPI_COLS;
+#pragma unroll 1                                                    // (unrolled, ptxas hoists the loads of every piece: the tile's values + 64 seeds live -> spills)
+            for (int c = 0; c < EPI_COLS / 16; c++) {
+                uint32_t sv[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) {
+                    const uint4 x = pi[c * 4 + j4];
+                    sv[4 * j4] = x.x; sv[4 * j4 + 1] = x.y; sv[4 * j4 + 2] = x.z; sv[4 * j4 + 3] = x.w;
+                }
+                tmem_st16(taddr + c * 16, sv);
+            }
+            tmem_wait_st();
+        };
+        auto release_accumulator = [&](uint32_t a) {                    // all epilogue warps -> accumulator free
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * a, 0));
+                else mbar_arrive(tempty0 + 8 * a);
+            }
+        };
+        auto item_tiles = [&](uint32_t w, uint32_t* a, uint32_t* b) {
+            const uint32_t c0 = (w / mgroups) * p.tiles_per_chunk;
+            *a = c0; *b = min(c0 + p.tiles_per_chunk, p.ntiles);
+        };
+        // Integer kinds: the CTA's tiles form ONE sequence across its work items (tile number i, parameter slot
+        // i % 3, accumulator i % 2) and the epilogue works ahead of the drain: parameters are published three
+        // tiles ahead, accumulators (INIT_ACC) are seeded two tiles ahead.
+        [[maybe_unused]] uint32_t la_t1 = 0;                              // end of the look-ahead cursor's item
+        auto seq_advance = [&](uint32_t* w, uint32_t* t) -> bool {       // false: the CTA has no further tile
+            if (*t + 1 < la_t1) { (*t)++; return true; }
+            *w += w_step;
+            if (*w >= items) return false;
+            uint32_t a;
+            item_tiles(*w, &a, &la_t1);                                   // (one integer division per work item, not per tile)
+            *t = a;
+            return true;
         };
         uint32_t acc = 0, acc_phase = 0;
-        [[maybe_unused]] long long st_total = 0, st_tfull = 0, st_compact = 0, st_tail = 0;
+        [[maybe_unused]] uint32_t seq_i = 0, seq_total = 0;             // running tile number / tiles of this CTA
+        [[maybe_unused]] uint32_t seq_slot = 0;                         // seq_i % 3, kept incrementally
+        [[maybe_unused]] uint32_t la_w = w_first, la_t = 0;             // look-ahead cursor: the next tile to publish
+        [[maybe_unused]] bool la_ok = w_first < items;
+        if (INT) {
+            for (uint32_t w = w_first; w < items; w += w_step) { uint32_t a, b; item_tiles(w, &a, &b); seq_total += b - a; }
+            if (la_ok) item_tiles(la_w, &la_t, &la_t1);
+            // prologue: tiles #0..#2 get their parameters; INIT_ACC seeds both accumulators (tiles #0, #1) and hands
+            // them to the issuer before any MMA is issued
+            for (uint32_t slot = 0; slot < 3; slot++) {
+                float raw[CPLANE]; uint32_t mw[CPLANE];
+#pragma unroll
+                for (int j = 0; j < CPLANE; j++) { raw[j] = 0.f; mw[j] = 0; }
+                if (la_ok) {
+#pragma unroll
+                    for (int j = 0; j < CPLANE; j++) load_raw(la_t, j, &raw[j], &mw[j]);
+                }
+                publish_params(slot, la_ok ? la_t : 0u, raw, mw);
+                if (la_ok) la_ok = seq_advance(&la_w, &la_t);
+            }
+            __syncwarp();
+            if (INIT_ACC) {
+                for (uint32_t a = 0; a < 2; a++) { seed_accumulator(a, a); release_accumulator(a); }
+            }
+        }
+        [[maybe_unused]] long long st_total = 0, st_tfull = 0, st_compact = 0, st_tail = 0, st_drain = 0, st_seed = 0, st_proc = 0, st_pub = 0;
         TC_STAT_BEGIN(c_all);
         for (uint32_t w = w_first; w < items; w += w_step) {
             const uint32_t mt = (w % mgroups) * CL + crank, ch = w / mgroups;
@@ -499,13 +631,15 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             // the strict case compares against the next smaller key.
             uint32_t thr_key = 0xffffffffu, loc_key = 0xffffffffu;
             float thr_f = __int_as_float(0x7f800000);                   // +inf: everything passes until k are known
-            // Integer spaces.  MODE 0 ranks s = |x|^2 - 2a: hit iff s <= thr_i.  MODE 1 ranks s = -a, but the
-            // epilogue never negates: it looks for the LARGEST a and a hit is a > ~thr_i (== -a <= thr_i for every
-            // thr_i, with no overflow at either end).  Besides saving 32 negations per group this keeps ptxas
-            // (12.9) from folding the negations into the 3-input minimum, which it does incorrectly: only the
-            // outer two operands of each VIMNMX3 came out negated and the early-out skipped real hits.
+            // Integer spaces never negate in the common path: they look for the LARGEST accumulator value.
+            //   dot (MODE 1): s = -a, a hit is a > ~t (== -a <= t for every t, no overflow at either end).  (Written as
+            //     min(-a0, -a1, -a2), ptxas 12.9 folded the negations into VIMNMX3 incorrectly and real hits were skipped.)
+            //   L2 (MODE 0, INIT_ACC): the tile holds r = a - (|x|^2 >> 1), s = (|x|^2 & 1) - 2r; s <= t implies
+            //     r >= -(t >> 1), so the common path looks for r > thr_i = -(t >> 1) - 1 and the exact test s <= thr_s
+            //     runs on the rare candidates only (no overflow: |t >> 1| <= 2^30).
             int thr_i = 0x7fffffff;
-            auto set_thr_i = [&](int t) { thr_i = (MODE == 0) ? t : ~t; };
+            [[maybe_unused]] int thr_s = 0x7fffffff;
+            auto set_thr_i = [&](int t) { if (INIT_ACC) { thr_s = t; thr_i = -(t >> 1) - 1; } else thr_i = ~t; };
             auto refresh_threshold = [&]() {
                 if (q >= p.nq) { thr_f = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }   // padding row of the query tile: nothing passes
                 if (thr_key == 0xffffffffu) { thr_f = __int_as_float(0x7f800000); set_thr_i(0x7fffffff); return; }
@@ -516,29 +650,45 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             };
             refresh_threshold();
             {
-                float* pr = my_prm + acc * EPI_COLS;
+                if (!INT) {                                              // (integer kinds: published three tiles ago)
+                    float raw0[CPLANE]; uint32_t mw0[CPLANE];
 #pragma unroll
-                for (int j = 0; j < CPLANE; j++) {
-                    bool live0;
-                    pr[j * 32 + lane] = load_param(t0, j, &live0);
-                    const unsigned vw0 = __ballot_sync(0xffffffffu, live0);
-                    if (lane == 0) my_valid[acc * CPLANE + j] = vw0;
+                    for (int j = 0; j < CPLANE; j++) load_raw(t0, j, &raw0[j], &mw0[j]);
+                    publish_params(acc, t0, raw0, mw0);
                 }
                 const uint32_t g0 = __ldcg(p.gthr + q);
                 if (g0 < thr_key) { thr_key = g0; refresh_threshold(); }
                 __syncwarp();
             }
+            // appends the candidates of one 32-column group whose bit is set in `mask` (rare per thread)
+            auto append_hits = [&](uint32_t mask, const uint32_t* v, uint32_t id0, uint32_t oddw) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if (mask & (1u << j)) {
+                        uint32_t key;
+                        if (INT) {
+                            // exact integer ranking value: s = (|x|^2 & 1) - 2r (L2) or -a (dot)
+                            const int s = INIT_ACC ? (int)((oddw >> j) & 1u) - 2 * (int)v[j] : -(int)v[j];
+                            if (INIT_ACC && s > thr_s) continue;       // passed the conservative bound on r only
+                            key = k::ordered_i32(s);
+                        } else {
+                            key = k::ordered_f32(__uint_as_float(v[j]));
+                        }
+                        mybuf[cnt++] = ((u64)key << 32) | (id0 + j);
+                    }
+                }
+            };
             for (uint32_t t = t0; t < t1; t++) {
-                const float* pr = my_prm + acc * EPI_COLS;
+                const uint32_t slot = INT ? seq_slot : acc;               // parameter slot of this tile
                 float nraw[CPLANE];
                 uint32_t nmw[CPLANE];
 #pragma unroll
                 for (int j = 0; j < CPLANE; j++) { nraw[j] = 0.f; nmw[j] = 0; }
-                if (t + 1 < t1) {
+                if (INT ? la_ok : (t + 1 < t1)) {
 #pragma unroll
-                    for (int j = 0; j < CPLANE; j++) load_raw(t + 1, j, &nraw[j], &nmw[j]);
+                    for (int j = 0; j < CPLANE; j++) load_raw(INT ? la_t : t + 1, j, &nraw[j], &nmw[j]);
                 }
-                const uint32_t* vs = my_valid + acc * CPLANE;
+                const uint32_t* vs = my_valid + slot * CPLANE;
                 // any CTA's k-th best for this query bounds the global k-th best: adopt the tightest seen.
                 // The word is read from L2 now and applied after this tile, so its latency is hidden.
                 const uint32_t gk = __ldcg(p.gthr + q);
@@ -546,79 +696,93 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 TC_STAT_ADD(st_tfull, c_w);
                 tcgen05_fence_after();
+                TC_STAT_BEGIN(c_d);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + grp * EPI_COLS;
-                for (int c2 = 0; c2 < EPI_COLS / (32 * LDG); c2++) {
-                    // LDG 32-column TMEM loads per wait (2 halves the exposed tcgen05.ld latency per tile)
-                    uint32_t vv[LDG][32];
+                if constexpr (INT) {
+                    // Integer kinds: once the LAST 32-column load of the tile has landed in registers
+                    // the accumulator is re-seeded for the tile two steps ahead (INIT_ACC) and handed back to the
+                    // issuer BEFORE its values are looked at: on short rows (config E: 512 MMA cycles per tile) the
+                    // chain tfull -> ld -> seed -> tempty is what the tensor pipe waits for, the max tree is not.
+                    constexpr int NCH = EPI_COLS / 32;
 #pragma unroll
-                    for (int hh = 0; hh < LDG; hh++) tmem_ld32(taddr + c2 * (32 * LDG) + hh * 32, vv[hh]);
-                    tmem_wait_ld();
+                    for (int cc = 0; cc < NCH; cc++) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + cc * 32, v);
+                        tmem_wait_ld();
+                        if (cc == NCH - 1) {
+                            TC_STAT_ADD(st_drain, c_d);
+                            TC_STAT_BEGIN(c_s);
+                            if (INIT_ACC && seq_i + 2 < seq_total) seed_accumulator(acc, seq_slot == 0 ? 2u : seq_slot - 1u);   // slot of tile i + 2
+                            release_accumulator(acc);
+                            TC_STAT_ADD(st_seed, c_s);
+                        }
+                        TC_STAT_BEGIN(c_p);
+                        const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
+                        int m0 = (int)0x80000000, m1 = (int)0x80000000;       // two chains: max of a (dot) / of r (L2)
 #pragma unroll
-                    for (int hh = 0; hh < LDG; hh++) {
-                    uint32_t (&v)[32] = vv[hh];
-                    const int cc = c2 * LDG + hh;
-                    const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
-                    const float4* pr4 = reinterpret_cast<const float4*>(pr + cc * 32);
-                    // ranking values in place, and their minimum: almost every 32-column group holds nothing that
-                    // beats the threshold, so the per-element compare + mask is only built when the minimum does
-                    float fmin_ = __int_as_float(0x7f800000);
-                    int iext_ = MODE == 0 ? 0x7fffffff : (int)0x80000000;     // min of s (MODE 0) / max of a (MODE 1)
+                        for (int j = 0; j < 32; j += 2) { m0 = max(m0, (int)v[j]); m1 = max(m1, (int)v[j + 1]); }
+                        uint32_t mask = 0;
+                        if (max(m0, m1) > thr_i) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
-                        const float4 pq = pr4[j4];
-                        const float pj[4] = {pq.x, pq.y, pq.z, pq.w};
+                            for (int j = 0; j < 32; j++) if ((int)v[j] > thr_i) mask |= 1u << j;
+                        }
+                        mask &= vs[cc];                                  // rows past the end, deleted or filtered out
+                        const uint32_t oddw = INIT_ACC ? my_odd[slot * CPLANE + cc] : 0u;
+                        if (p.dump) {
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int j = j4 * 4 + e;
-                            if (INT) {
-                                const int a = (int)v[j];
-                                if (MODE == 0) {
-                                    const int s = __float_as_int(pj[e]) - 2 * a;
-                                    v[j] = (uint32_t)s;
-                                    iext_ = min(iext_, s);
-                                } else {
-                                    iext_ = max(iext_, a);
+                            for (int j = 0; j < 32; j++)
+                                p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] =
+                                    (float)(INIT_ACC ? (int)((oddw >> j) & 1u) - 2 * (int)v[j] : -(int)v[j]);
+                        }
+                        if (mask) append_hits(mask, v, id0, oddw);
+                        TC_STAT_ADD(st_proc, c_p);
+                    }
+                } else {
+                    const float* pr = my_prm + slot * EPI_COLS;
+                    for (int c2 = 0; c2 < EPI_COLS / (32 * LDG); c2++) {
+                        // LDG 32-column TMEM loads per wait
+                        uint32_t vv[LDG][32];
+#pragma unroll
+                        for (int hh = 0; hh < LDG; hh++) tmem_ld32(taddr + c2 * (32 * LDG) + hh * 32, vv[hh]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int hh = 0; hh < LDG; hh++) {
+                            uint32_t (&v)[32] = vv[hh];
+                            const int cc = c2 * LDG + hh;
+                            const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
+                            // ranking values in place, and their minimum: almost every 32-column group holds nothing that
+                            // beats the threshold, so the per-element compare + mask is only built when the minimum does
+                            float fmin_ = __int_as_float(0x7f800000);
+                            const float4* pr4 = reinterpret_cast<const float4*>(pr + cc * 32);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; j4++) {
+                                const float4 pq = pr4[j4];
+                                const float pj[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const int j = j4 * 4 + e;
+                                    const float a = __uint_as_float(v[j]);
+                                    const float s = MODE == 0 ? fmaf(a, -2.0f, pj[e]) : a * pj[e];
+                                    v[j] = __float_as_uint(s);
+                                    fmin_ = fminf(fmin_, s);
                                 }
-                            } else {
-                                const float a = __uint_as_float(v[j]);
-                                const float s = MODE == 0 ? fmaf(a, -2.0f, pj[e]) : a * pj[e];
-                                v[j] = __float_as_uint(s);
-                                fmin_ = fminf(fmin_, s);
                             }
-                        }
-                    }
-                    uint32_t mask = 0;
-                    if (INT ? (MODE == 0 ? iext_ <= thr_i : iext_ > thr_i) : (fmin_ <= thr_f)) {
+                            uint32_t mask = 0;
+                            if (fmin_ <= thr_f) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if (INT) { if (MODE == 0 ? (int)v[j] <= thr_i : (int)v[j] > thr_i) mask |= 1u << j; }
-                            else { if (__uint_as_float(v[j]) <= thr_f) mask |= 1u << j; }
-                        }
-                    }
-                    mask &= vs[cc];                                      // rows past the end, deleted or filtered out
-                    if (p.dump) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] =
-                                INT ? (float)(MODE == 0 ? (int)v[j] : -(int)v[j]) : __uint_as_float(v[j]);
-                    }
-                    if (mask) {                                          // rare per thread
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if (mask & (1u << j)) {
-                                const uint32_t key = INT ? k::ordered_i32(MODE == 0 ? (int)v[j] : -(int)v[j])
-                                                         : k::ordered_f32(__uint_as_float(v[j]));
-                                mybuf[cnt++] = ((u64)key << 32) | (id0 + j);
+                                for (int j = 0; j < 32; j++) if (__uint_as_float(v[j]) <= thr_f) mask |= 1u << j;
                             }
+                            mask &= vs[cc];                              // rows past the end, deleted or filtered out
+                            if (p.dump) {
+#pragma unroll
+                                for (int j = 0; j < 32; j++)
+                                    p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = __uint_as_float(v[j]);
+                            }
+                            if (mask) append_hits(mask, v, id0, 0u);
                         }
                     }
-                    }
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) {                                         // all epilogue warps -> accumulator free
-                    if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty0 + 8 * acc, 0));
-                    else mbar_arrive(tempty0 + 8 * acc);
+                    TC_STAT_ADD(st_drain, c_d);
+                    release_accumulator(acc);
                 }
                 // A buffer past its trigger level is compacted now, by the whole warp -- after the accumulator went back to
                 // the issuer, so the sort overlaps the next tiles' MMAs instead of holding up every other warp's tile.
@@ -649,17 +813,18 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 }
                 if (gk < thr_key) { thr_key = gk; refresh_threshold(); }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (t + 1 < t1) {                                          // publish the next tile's parameters (warp-private)
-                    float* prn = my_prm + acc * EPI_COLS;
-#pragma unroll
-                    for (int j = 0; j < CPLANE; j++) {
-                        bool lv;
-                        prn[j * 32 + lane] = finish_param(t + 1, j, nraw[j], nmw[j], &lv);
-                        const unsigned vw = __ballot_sync(0xffffffffu, lv);
-                        if (lane == 0) my_valid[acc * CPLANE + j] = vw;
-                    }
+                TC_STAT_BEGIN(c_u);
+                if (INT) {
+                    // the slot this tile just vacated takes the parameters of the tile three steps ahead
+                    __syncwarp();
+                    if (la_ok) { publish_params(slot, la_t, nraw, nmw); la_ok = seq_advance(&la_w, &la_t); }
+                    seq_i++;
+                    seq_slot = seq_slot == 2 ? 0u : seq_slot + 1u;
+                } else if (t + 1 < t1) {
+                    publish_params(acc, t + 1, nraw, nmw);                 // the next tile's parameters (warp-private)
                 }
                 __syncwarp();
+                TC_STAT_ADD(st_pub, c_u);
             }
             // end of the work item: every query's buffer becomes a sorted list of its k best
             TC_STAT_BEGIN(c_tail);
@@ -684,6 +849,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         if (p.stats && lane == 0 && warp == 2) {
             atomicAdd(p.stats + 6, (unsigned long long)st_total); atomicAdd(p.stats + 7, (unsigned long long)st_tfull);
             atomicAdd(p.stats + 8, (unsigned long long)st_compact); atomicAdd(p.stats + 9, (unsigned long long)st_tail);
+            atomicAdd(p.stats + 10, (unsigned long long)st_drain); atomicAdd(p.stats + 11, (unsigned long long)st_seed);
+            atomicAdd(p.stats + 12, (unsigned long long)st_proc); atomicAdd(p.stats + 13, (unsigned long long)st_pub);
         }
 #endif
     }

@@ -140,8 +140,11 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
         TC_CUDA_CHECK(cudaMemcpy(h, st.stats.p, sizeof(h), cudaMemcpyDeviceToHost));
         auto pct = [&](int part, int whole) { return h[whole] ? 100.0 * (double)h[part] / (double)h[whole] : 0.0; };
         std::fprintf(stderr, "[tc stats] producer: wait-empty %.1f%% pacing %.1f%% | issuer: wait-full %.1f%% wait-accumulator %.1f%% | "
-                             "epilogue warp: wait-accumulator-ready %.1f%% compaction %.1f%% item-tail %.1f%%\n",
-                     pct(1, 0), pct(2, 0), pct(4, 3), pct(5, 3), pct(7, 6), pct(8, 6), pct(9, 6));
+                             "epilogue warp: wait-accumulator-ready %.1f%% drain %.1f%% seed+handback %.1f%% process %.1f%% publish %.1f%% compaction %.1f%% item-tail %.1f%% | "
+                             "cycles per tile-job: %.0f (grid %u, %u tiles x %u query tiles)\n",
+                     pct(1, 0), pct(2, 0), pct(4, 3), pct(5, 3), pct(7, 6), pct(10, 6), pct(11, 6), pct(12, 6), pct(13, 6), pct(8, 6), pct(9, 6),
+                     (double)h[6] / ((double)ntiles * (double)mtiles),      // every CTA's warp 2 adds its total; a CTA runs ntiles * mtiles / grid tile-jobs
+                     grid, ntiles, mtiles);
     }
 #endif
     SearchResult r;

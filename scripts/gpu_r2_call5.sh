@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q -x --timeout 300 --timeout-method thread 2>&1 | tail -5
+timeout 600 python -m pytest "tests/test_gpu_fullsize.py" -m gpu -q -x -k "tensor" --timeout 300 --timeout-method thread 2>&1 | tail -5
+echo "== E1024 slab (product build)"
+timeout 300 python scripts/bench_summary.py E1024 --steps 5 --warmup 3 --rows 100000000
+MVF_B200_LIB=$PWD/metrovector_b200/libmvf_b200_stats.so timeout 300 python bench.py --workload E1024 --rows 100000000 --steps 3 --warmup 3 --no-cpu 2>&1 | grep "tc stats" | tail -1

@@ -1,8 +1,7 @@
 #!/bin/bash
-# diagnostic build (-DMVF_TC_STATS): per-role cycle breakdown of the tensor kernel on the batched configs
-for W in "C" "D1024 --rows 20000000" "E1024 --rows 100000000"; do
+# diagnostic build (-DMVF_TC_STATS, metrovector_b200/libmvf_b200_stats.so): per-role cycle breakdown of the tensor kernel
+export MVF_B200_LIB=$PWD/metrovector_b200/libmvf_b200_stats.so
+for W in "E1024 --rows 100000000" "D1024 --rows 20000000" "C" "B1024"; do
 echo "== $W"
-timeout 300 python bench.py --workload $W --steps 3 --warmup 2 --no-cpu 2>&1 | grep "tc stats" | tail -3
+timeout 300 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu 2>&1 | grep "tc stats" | tail -2
 done
-echo "== C multicast"; MVF_TC_PAIR=0 timeout 300 python bench.py --workload C --steps 3 --warmup 2 --no-cpu 2>&1 | grep "tc stats" | tail -2
-echo "== C no pacing"; MVF_TC_SYNC_WINDOW=0 timeout 300 python bench.py --workload C --steps 3 --warmup 2 --no-cpu 2>&1 | grep "tc stats" | tail -2

@@ -268,8 +268,17 @@ def test_device_crc32_matches_zlib_and_the_block_manifest(engine, tmp_path):
         crc, ms = gs.checksum()
         assert crc == (zlib.crc32(db.tobytes()) & 0xFFFFFFFF), (dtype, n, d)
         gs.free()
-    with pytest.raises(mv.Build):                                   # ragged rows are padded in HBM: host check only
-        engine.from_host(mv.synth_fill_host(oracle.U8, 1, 0, 10, 13), mv.DataType.UInt8, mv.DistanceMetric.L2).checksum()
+    # ragged rows (row bytes not a multiple of 16) are padded in HBM: the kernel hashes one row per thread and skips the padding
+    for dtype, n, d in ((oracle.U8, 10, 13), (oracle.F16, 5003, 100), (oracle.I8, 70_001, 129), (oracle.F32, 999, 5)):
+        db = mv.synth_fill_host(dtype, 83, 0, n, d)
+        gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+        assert gs.checksum()[0] == (zlib.crc32(db.tobytes()) & 0xFFFFFFFF), (dtype, n, d)
+        gs.free()
+    # a shard of a larger space cannot vouch for the whole block without a communicator
+    part = engine.from_host(mv.synth_fill_host(oracle.U8, 1, 0, 10, 16), mv.DataType.UInt8, mv.DistanceMetric.L2, row_base=5, global_n=40)
+    with pytest.raises(mv.Build):
+        part.checksum()
+    part.free()
     rows = mv.synth_fill_host(oracle.F32, 82, 0, 5000, 64)
     b = mv.MvfBuilder()
     b.add_vector_space("v", 64, mv.VectorType.Dense, mv.DistanceMetric.L2, mv.DataType.Float32)
