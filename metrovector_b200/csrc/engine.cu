@@ -114,6 +114,8 @@ struct mvf_gpu {
     uint64_t scan_launches = 0, all_launches = 0;
     int last_path = 0;
     int ctas_per_sm_cap = 0;   // MVF_SCAN_CTAS_PER_SM, 0 = occupancy
+    DevBuf scan_counter;                   // "CTAs done" word of the fused K1 + K3 launch (zero between launches)
+    bool no_fused_merge = false;           // MVF_NO_FUSED_MERGE: always launch K3 separately (A/B)
     DevBuf cand, packed_local, gathered, queries, out_ids, out_scores, out_iscores, merge_tmp[2], gather_ids, gather_out, crc_tables, scalar_tmp;
     mvf_gpu* parent_group = nullptr;       // set on the members of a group engine
     int merge_tmp_flip = 0;
@@ -222,7 +224,7 @@ template <int DT> size_t scan_smem(int NQ, uint32_t P, uint32_t dpad) {
     return (size_t)NQ * P * 8 + ((q_bytes + 15) & ~(size_t)15) + (size_t)NQ * sizeof(k::QueryConst) + 64;
 }
 
-void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out);
+bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out, k::MergeParams* fuse);
 size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
     switch (dtype) {
         case k::DT_F32: return scan_smem<k::DT_F32>(NQ, P, scan_shape<k::DT_F32>(pitch).dpad);
@@ -232,7 +234,11 @@ size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
     }
 }
 
-void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out) {
+// Launches K1.  With `fuse` (the K3 parameters of the same launch, `in`/`q_stride`/`nlists` filled in here) the
+// per-CTA lists are merged by the last CTA of the SAME launch whenever they fit its shared memory (<= 1024 lists,
+// <= 96 KiB): one launch per search instead of two -- what the latency-bound configs are made of.  Returns whether
+// the merge was fused; if not the caller launches K3.
+bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out, k::MergeParams* fuse) {
     ScanShape sh;
     const void* fn = nullptr;
     const int op = p.metric == k::M_L2 ? k::OP_L2 : k::OP_DOT;
@@ -242,21 +248,44 @@ void launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, ui
         case k::DT_I8: sh = scan_shape<k::DT_I8>(s->pitch); fn = k::scan_kernel_i8(op, NQ, sh.wide); break;
         default: sh = scan_shape<k::DT_U8>(s->pitch); fn = k::scan_kernel_u8(op, NQ, sh.wide); break;
     }
-    const size_t smem = scan_smem_any(s->dtype, NQ, p.P, s->pitch);
+    size_t smem = scan_smem_any(s->dtype, NQ, p.P, s->pitch);
     int nb = occupancy(g, fn, k::kScanThreads, smem);
     if (g->ctas_per_sm_cap > 0) nb = std::min(nb, g->ctas_per_sm_cap);
     const int R = k::scan_rows_in_flight(NQ);
     const uint64_t rows_per_group = sh.wide ? (uint64_t)R : (uint64_t)R * (32 / sh.LPR);
     const uint64_t groups = (s->local_n + rows_per_group - 1) / rows_per_group;
     const uint64_t want = (groups + k::kScanWarps - 1) / k::kScanWarps;
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb, want));
+    uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb, want));
+    k::ScanTail tail;
+    tail.counter = nullptr;
+    bool fused = false;
+    if (fuse && !g->no_fused_merge) {
+        auto merge_smem = [&](uint32_t lists) { return ((size_t)lists + k::kScanWarps) * p.k * 8 + 16; };
+        size_t smem_f = std::max(smem, merge_smem(grid));
+        if (smem_f <= 96 * 1024) {
+            int nb_f = occupancy(g, fn, k::kScanThreads, smem_f);          // a larger allocation may cost resident CTAs
+            if (g->ctas_per_sm_cap > 0) nb_f = std::min(nb_f, g->ctas_per_sm_cap);
+            const uint32_t grid_f = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb_f, want));
+            if (grid_f <= 1024 && grid_f <= grid) {
+                grid = grid_f; smem = smem_f; fused = true;
+                if (!g->scan_counter.p) {
+                    g->scan_counter.reserve(16);
+                    CUDA_CHECK(cudaMemsetAsync(g->scan_counter.p, 0, 16, g->stream));
+                }
+                fuse->in = p.cand; fuse->q_stride = (size_t)grid * p.k; fuse->list_stride = p.k; fuse->nlists = grid;
+                tail.counter = (uint32_t*)g->scan_counter.p;
+                tail.mp = *fuse;
+            }
+        }
+    }
     *grid_out = grid;
     ScanTimer t(g);
     int lpr = sh.LPR;
-    void* args_wide[] = {(void*)&p};
-    void* args_narrow[] = {(void*)&p, (void*)&lpr};
+    void* args_wide[] = {(void*)&p, (void*)&tail};
+    void* args_narrow[] = {(void*)&p, (void*)&lpr, (void*)&tail};
     CUDA_CHECK(cudaLaunchKernel(fn, dim3(grid), dim3(k::kScanThreads), sh.wide ? args_wide : args_narrow, smem, g->stream));
     g->scan_launches++; g->all_launches++;
+    return fused;
 }
 
 void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
@@ -445,9 +474,9 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         p.rows = s->rows; p.norm = s->norm; p.mask = s->mask; p.queries = d_queries; p.cand = (u64*)g->cand.p;
         p.n = s->local_n; p.d = s->d; p.pitch = s->pitch; p.k = kk; p.P = P; p.metric = metric; p.qdtype = qdtype; p.q0 = q0;
         uint32_t grid = 0;
-        if (s->local_n > 0) launch_scan(g, s, p, NQ, &grid);
         k::MergeParams mp;
-        mp.in = (const u64*)g->cand.p; mp.q_stride = (size_t)grid * kk; mp.list_stride = kk; mp.nlists = grid; mp.k = kk;
+        mp.in = (const u64*)g->cand.p; mp.q_stride = 0; mp.list_stride = kk; mp.nlists = 0; mp.k = kk;
+        mp.P = 0; mp.seg_lists = 0;
         mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 0; mp.qconst = nullptr;
         const size_t o = (size_t)q0 * kk;
         mp.out_packed = multi ? packed_local + o : nullptr;
@@ -455,7 +484,12 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         mp.out_scores = multi ? nullptr : (d_scores ? d_scores + o : nullptr);
         mp.out_iscores = multi ? nullptr : (d_iscores ? d_iscores + o : nullptr);
         mp.ext_ids = s->ext_ids;
-        launch_merge(g, mp, (uint32_t)NQ);
+        bool fused = false;
+        if (s->local_n > 0) fused = launch_scan(g, s, p, NQ, &grid, &mp);
+        if (!fused) {
+            mp.q_stride = (size_t)grid * kk; mp.nlists = grid;
+            launch_merge(g, mp, (uint32_t)NQ);
+        }
         q0 += (uint32_t)NQ;
     }
 }
@@ -826,6 +860,7 @@ mvf_gpu* create_engine(int device) {
     if (se != cudaSuccess) { delete g; CUDA_CHECK(se); }
     g->own_stream = true;
     if (const char* c = std::getenv("MVF_SCAN_CTAS_PER_SM")) g->ctas_per_sm_cap = std::atoi(c);
+    if (std::getenv("MVF_NO_FUSED_MERGE")) g->no_fused_merge = true;
     if (const char* c = std::getenv("MVF_UPLOAD_THREADS")) g->upload_threads = std::max(1, std::min(16, std::atoi(c)));
     try { mvf::tc::init(g->tc); } catch (...) { /* the tensor path reports its own error when it is first used */ }
     return g;
@@ -841,7 +876,7 @@ void destroy_engine(mvf_gpu* g) {
         for (auto& e : g->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         g->cand.release(); g->packed_local.release(); g->gathered.release(); g->queries.release();
         g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release();
-        g->gather_ids.release(); g->gather_out.release(); g->crc_tables.release(); g->scalar_tmp.release();
+        g->gather_ids.release(); g->gather_out.release(); g->crc_tables.release(); g->scalar_tmp.release(); g->scan_counter.release();
         mvf::tc::release(g->tc);
         if (g->pinned_out) cudaFreeHost(g->pinned_out);
         if (g->pinned_flag) cudaFreeHost(g->pinned_flag);

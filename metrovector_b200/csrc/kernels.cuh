@@ -183,29 +183,6 @@ __device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, ui
     }
 }
 
-#ifdef MVF_ENGINE_TU   // non-template kernels: defined in engine.cu's translation unit only
-__global__ void __launch_bounds__(1024) merge_topk(const MergeParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    u64* buf = reinterpret_cast<u64*>(smem);
-    const uint32_t q = blockIdx.x, tid = threadIdx.x;
-    const size_t total = (size_t)p.nlists * p.k;
-    const u64* src = p.in + (size_t)q * p.q_stride;
-    for (uint32_t i = tid; i < p.k; i += blockDim.x) buf[i] = kInf;
-    size_t done = 0;
-    do {
-        const uint32_t room = p.P - p.k;
-        for (uint32_t i = tid; i < room; i += blockDim.x) {
-            size_t c = done + i;
-            u64 v = kInf;
-            if (c < total) v = src[(c / p.k) * p.list_stride + (c % p.k)];
-            buf[p.k + i] = v;
-        }
-        done += room;
-        block_bitonic_sort(buf, (int)p.P, (int)tid, (int)blockDim.x);
-    } while (done < total);
-    for (uint32_t j = tid; j < p.k; j += blockDim.x) emit_result(p, q, j, buf[j]);
-}
-
 // K3, fast flavour: the lists are individually sorted, so the k best of their union come out of a
 // two-level tournament.  All nlists*k words are staged in shared memory; each of the 32 warps
 // merges its share of the lists (one or more list heads per lane, warp-min per output), then warp 0
@@ -253,6 +230,35 @@ __device__ __forceinline__ void warp_tournament(const u64* base, size_t stride, 
         }
     }
     __syncwarp();
+}
+
+// K1 + K3 in one launch: what the scan kernels need to merge their own per-CTA lists (the last CTA to finish does it)
+struct ScanTail {
+    uint32_t* counter;        // CTAs finished so far (zero between launches); nullptr = no fused merge, K3 is launched separately
+    MergeParams mp;           // in / q_stride / nlists describe ScanParams::cand of the same launch
+};
+
+#ifdef MVF_ENGINE_TU   // non-template kernels: defined in engine.cu's translation unit only
+__global__ void __launch_bounds__(1024) merge_topk(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64* buf = reinterpret_cast<u64*>(smem);
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const size_t total = (size_t)p.nlists * p.k;
+    const u64* src = p.in + (size_t)q * p.q_stride;
+    for (uint32_t i = tid; i < p.k; i += blockDim.x) buf[i] = kInf;
+    size_t done = 0;
+    do {
+        const uint32_t room = p.P - p.k;
+        for (uint32_t i = tid; i < room; i += blockDim.x) {
+            size_t c = done + i;
+            u64 v = kInf;
+            if (c < total) v = src[(c / p.k) * p.list_stride + (c % p.k)];
+            buf[p.k + i] = v;
+        }
+        done += room;
+        block_bitonic_sort(buf, (int)p.P, (int)tid, (int)blockDim.x);
+    } while (done < total);
+    for (uint32_t j = tid; j < p.k; j += blockDim.x) emit_result(p, q, j, buf[j]);
 }
 
 __global__ void __launch_bounds__(1024) merge_topk_tournament(const MergeParams p) {

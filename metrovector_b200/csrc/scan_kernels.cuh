@@ -110,6 +110,42 @@ __device__ __forceinline__ void emit_cta_lists(const ScanParams& p, u64* lists) 
     }
 }
 
+// K1 + K3 fused (latency-bound configs: BASELINE configs[0] is 51 MB, 8 us of HBM time against two launches and a
+// dependent grid start): every CTA counts itself done after its lists are visible; the last one stages all
+// gridDim.x lists of a query in shared memory and runs the same two-level warp tournament as merge_topk_tournament,
+// decoding straight into the caller's outputs.  The host only asks for this when the lists fit (engine.cu).
+template <int NQ>
+__device__ __forceinline__ void fused_merge_tail(const ScanParams& p, const ScanTail& tail, unsigned char* smem) {
+    if (tail.counter == nullptr) return;
+    __shared__ uint32_t s_last;
+    __threadfence();                                        // this CTA's lists are visible before it is counted
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(tail.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *tail.counter = 0;                // zero again for the next launch on this stream
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nlists = gridDim.x, k = p.k;
+    u64* cand_s = reinterpret_cast<u64*>(smem);             // [nlists][k]
+    u64* lvl1 = cand_s + (size_t)nlists * k;                // [kScanWarps][k]
+    const uint32_t per = (nlists + kScanWarps - 1) / kScanWarps;
+    const uint32_t l0 = warp * per;
+    const uint32_t nl = l0 < nlists ? min(per, nlists - l0) : 0;
+    for (int q = 0; q < NQ; q++) {
+        const u64* src = p.cand + (size_t)q * nlists * k;
+        const uint32_t total = nlists * k;
+        for (uint32_t c = threadIdx.x; c < total; c += blockDim.x) cand_s[c] = __ldcg(src + c);   // other CTAs wrote them: read at L2
+        __syncthreads();
+        warp_tournament(cand_s + (size_t)l0 * k, k, nl, k, lvl1 + (size_t)warp * k, (int)lane);
+        __syncthreads();
+        if (warp == 0) {
+            warp_tournament(lvl1, k, kScanWarps, k, cand_s, (int)lane);
+            for (uint32_t j = lane; j < k; j += 32) emit_result(tail.mp, (uint32_t)q, j, cand_s[j]);
+        }
+        __syncthreads();
+    }
+}
+
 // Transposed warp reduction.  Every lane enters with R partial sums (one per row of the group);
 // the lanes of each LPR-lane team leave with the team totals spread over them: while more than one
 // value is left, a step at offset OFF halves the value count (each lane keeps the half selected
@@ -178,7 +214,7 @@ __device__ __forceinline__ void offer(u64 pk, u64* list, int k, u64& thr, int& p
 // R loads in flight all the time.  The resident buffer carries kPadRows zero rows past the end
 // (engine.cu), so the last partial group needs no clamping; rows >= n are dropped before insert.
 template <int DT, int OP, int NQ, int R>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanParams p, const ScanTail tail) {
     constexpr int EPC = Traits<DT>::EPC;
     constexpr bool F = Traits<DT>::is_float;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -334,6 +370,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
         for (int q = 0; q < NQ; q++) if (lane < (int)p.k) lists[(size_t)q * p.P + warp * p.k + lane] = regl[q];
     }
     emit_cta_lists<NQ>(p, lists);
+    fused_merge_tail<NQ>(p, tail, smem);
 }
 
 // NARROW rows (<= 16 chunks): LPR = pow2 >= chunks lanes per row, 32/LPR rows per warp load,
@@ -476,7 +513,7 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
 }
 
 template <int DT, int OP, int NQ, int R>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_narrow(const ScanParams p, const int LPR) {
+__global__ void __launch_bounds__(kScanThreads, 2) scan_topk_narrow(const ScanParams p, const int LPR, const ScanTail tail) {
     constexpr int EPC = Traits<DT>::EPC;
     constexpr bool F = Traits<DT>::is_float;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -496,6 +533,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_narrow(const ScanPa
         default: narrow_body<DT, OP, NQ, R, 16>(p, lists, q_s, dpad, qc_s); break;
     }
     emit_cta_lists<NQ>(p, lists);
+    fused_merge_tail<NQ>(p, tail, smem);
 }
 
 // kernel lookup for one data type (called from engine.cu through scan_kernel_for())
