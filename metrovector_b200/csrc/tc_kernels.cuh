@@ -42,7 +42,8 @@ struct TcParams {
     u64* cand;                     // [gridDim.x][EG][BM][cap] scratch candidate buffers
     u64* out_lists;                // [nq][chunks*EG][k] sorted lists (key = ordered ranking value, id = local row)
     float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
-    uint32_t* gthr;                // [(mtiles rounded up to the cluster size)*BM] tightest k-th-best key any CTA has seen per query (atomicMin)
+    uint32_t* gthr;                // [(mtiles rounded up to the cluster size)*BM] tightest bound on the k-th-best key any CTA has established per query (atomicMin)
+    uint32_t* gslot;               // [same rows][TC_SLOTS] best ceil(k / TC_SLOTS)-th key of the lists in each slot class (see share_bound)
     uint64_t n;                    // resident rows
     uint32_t nq, k, cap;
     uint32_t trigger;              // a buffer holding more than this many entries after a tile is compacted (<= cap - columns per thread)
@@ -252,9 +253,29 @@ __device__ __forceinline__ void warp_bitonic_sort(u64* a, int P, int lane) {
     __syncwarp();
 }
 
+// Cross-list threshold.  A query's rows are cut into many independent lists (work items x column groups); a list's own
+// k-th best only bounds the global k-th best as tightly as ITS slice of the rows allows (config C: 74 lists of 135k
+// rows each, so every list kept collecting ~k candidates of its own).  Lists are disjoint sets of rows, so if each of
+// TC_SLOTS different lists holds j = ceil(k / TC_SLOTS) rows with key <= T, at least k rows do: T bounds the global k-th
+// best.  Every list publishes its j-th best into slot (list % TC_SLOTS) by atomicMin (a slot keeps the best j-th key
+// of its class; values only fall, so a stale read is merely conservative) and whoever publishes folds the maximum of
+// the slots into gthr, where every CTA already looks.
+constexpr int TC_SLOTS = 8;
+__device__ __forceinline__ void share_bound(const TcParams& p, uint32_t q, uint32_t list, uint32_t kth_key, bool have_kth,
+                                            uint32_t jth_key, bool have_jth) {
+    if (have_kth) atomicMin(p.gthr + q, kth_key);
+    if (!have_jth) return;
+    uint32_t* slots = p.gslot + (size_t)q * TC_SLOTS;
+    atomicMin(slots + (list % TC_SLOTS), jth_key);
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < TC_SLOTS; i++) t = max(t, __ldcg(slots + i));       // 0xffffffff while a class has not published
+    if (t != 0xffffffffu) atomicMin(p.gthr + q, t);
+}
+
 // Compacts the candidate buffer of one query (owned by lane `owner` of this warp) to its k best,
 // sorted ascending; returns the new entry count and the k-th best word (kInf while fewer than k).
-__device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap, u64* scratch, int lane, int* new_cnt) {
+__device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap, u64* scratch, int lane, int* new_cnt, u64* jth = nullptr) {
     int P = 32;
     while (P < cnt) P <<= 1;
     if (P > cap) P = cap;
@@ -263,6 +284,7 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
     const int keep = cnt < k ? cnt : k;
     for (int i = lane; i < keep; i += 32) gbuf[i] = scratch[i];
     const u64 kth = (cnt >= k) ? scratch[k - 1] : kInf;
+    if (jth) { const int j = (k + TC_SLOTS - 1) / TC_SLOTS; *jth = (cnt >= j) ? scratch[j - 1] : kInf; }   // see share_bound
     __syncwarp();
     *new_cnt = keep;
     return kth;
@@ -797,7 +819,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         u64* obuf = cta_cand + (size_t)(quarter * 32 + owner) * p.cap;
                         __syncwarp();
                         int ncnt;
-                        const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
+                        u64 jth;
+                        const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt, &jth);
                         if (lane == owner) {
                             cnt = ncnt;
                             if (kth != kInf) {
@@ -805,8 +828,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                                 loc_key = kk;
                                 if (kk < thr_key) thr_key = kk;
                                 refresh_threshold();
-                                atomicMin(p.gthr + q, kk);
                             }
+                            share_bound(p, q, ch * EPI_GROUPS + grp, (uint32_t)(kth >> 32), kth != kInf, (uint32_t)(jth >> 32), jth != kInf);
                         }
                     }
                     TC_STAT_ADD(st_compact, c_c);
@@ -833,9 +856,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 u64* obuf = cta_cand + (size_t)(quarter * 32 + owner) * p.cap;
                 __syncwarp();
                 int ncnt;
-                const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt);
+                u64 jth;
+                const u64 kth = compact_buffer(obuf, ocnt, (int)p.k, (int)p.cap, wscratch, lane, &ncnt, &jth);
                 const uint32_t qo = mt * BM + quarter * 32 + owner;
-                if (lane == 0 && kth != kInf) atomicMin(p.gthr + qo, (uint32_t)(kth >> 32));
+                if (lane == 0) share_bound(p, qo, ch * EPI_GROUPS + grp, (uint32_t)(kth >> 32), kth != kInf, (uint32_t)(jth >> 32), jth != kInf);
                 if (qo < p.nq) {
                     u64* dst = p.out_lists + ((size_t)qo * (p.chunks * EPI_GROUPS) + ch * EPI_GROUPS + grp) * p.k;
                     for (int i = lane; i < (int)p.k; i += 32) dst[i] = i < ncnt ? wscratch[i] : kInf;

@@ -51,8 +51,10 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
     st.qconst.reserve((size_t)a.nq * 4);
     st.cand.reserve((size_t)grid * EG * BM * cap * 8);
     st.lists.reserve((size_t)a.nq * chunks * EG * a.k * 8);
-    st.gthr.reserve((size_t)mgroups * CL * BM * 4);
-    TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, (size_t)mgroups * CL * BM * 4, stream));
+    // per-query bounds shared by all CTAs: gthr [rows] followed by gslot [rows][TC_SLOTS], all "nothing known yet"
+    const size_t bound_rows = (size_t)mgroups * CL * BM;
+    st.gthr.reserve(bound_rows * 4 * (1 + TC_SLOTS));
+    TC_CUDA_CHECK(cudaMemsetAsync(st.gthr.p, 0xff, bound_rows * 4 * (1 + TC_SLOTS), stream));
     if (sync_window) {
         st.progress.reserve((size_t)items * 4);
         TC_CUDA_CHECK(cudaMemsetAsync(st.progress.p, 0, (size_t)items * 4, stream));
@@ -94,6 +96,7 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
     TcParams p;
     p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
+    p.gslot = p.gthr + bound_rows;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
     p.trigger = pl.trigger;
     p.kblocks = kblocks;
