@@ -149,6 +149,7 @@ struct mvf_gpu_space {
     uint64_t masked_rows = 0;
     std::vector<uint32_t> mask_part[2];   // host copies of the two components, local rows: [0] tombstones, [1] filter
     uint64_t* ext_ids = nullptr;          // optional external id per GLOBAL row (vector_ids_block_index)
+    int* acc_seed = nullptr;              // integer spaces: accumulator seeds of the tensor path's L2 form (built on first use, dropped when the mask changes)
     unsigned char* rows_split = nullptr;  // Float32 spaces: the two tf32-exact planes [hi | lo] the batched path multiplies (K2')
     // Facts every rank of a sharded space agrees on (exchanged at upload): ranks that chose different kernels would
     // exchange candidate keys in different encodings.
@@ -436,7 +437,15 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         if (qfinite == QF_NONFINITE) use_tc = false;
     }
     if (use_tc) {
+        if ((s->dtype == k::DT_I8 || s->dtype == k::DT_U8) && metric == k::M_L2 && !s->acc_seed && s->local_n) {
+            const uint64_t padded = ((s->local_n + mvf::tc::BN - 1) / mvf::tc::BN) * mvf::tc::BN;
+            CUDA_CHECK(cudaMalloc((void**)&s->acc_seed, padded * 4));
+            k::build_acc_seed<<<(uint32_t)g->sm_count * 8, 256, 0, g->stream>>>(s->sq, s->mask, s->local_n, padded, (int)0x80000000 + (1 << 25), s->acc_seed);
+            CUDA_CHECK(cudaGetLastError());
+            g->all_launches++;
+        }
         mvf::tc::SearchArgs a;
+        a.acc_seed = s->acc_seed;
         a.rows = s->rows; a.rows_split = s->rows_split; a.norm = s->norm; a.sq = s->sq; a.mask = s->mask; a.n = s->local_n; a.d = s->d;
         a.pitch = s->pitch; a.dtype = s->dtype; a.metric = metric; a.queries = d_queries; a.nq = nq; a.k = kk; a.dump = false;
         mvf::tc::SearchResult r;
@@ -802,6 +811,7 @@ void set_mask_part(mvf_gpu_space* s, int part, const uint8_t* bitmap, uint64_t n
             mine[w] = v;
         }
     }
+    if (s->acc_seed) { cudaFree(s->acc_seed); s->acc_seed = nullptr; }    // they encode the mask: rebuilt on the next tensor-path search
     const std::vector<uint32_t>& a = s->mask_part[0];
     const std::vector<uint32_t>& b = s->mask_part[1];
     if (a.empty() && b.empty()) { cudaFree(s->mask); s->mask = nullptr; s->masked_rows = 0; return; }
@@ -833,7 +843,7 @@ void free_space(mvf_gpu_space* s) {
     for (mvf_gpu_space* sh : s->shards) free_space(sh);
     if (!s->is_group()) {
         cudaSetDevice(s->g->device);
-        cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask); cudaFree(s->ext_ids); cudaFree(s->rows_split);
+        cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask); cudaFree(s->ext_ids); cudaFree(s->rows_split); cudaFree(s->acc_seed);
     }
     delete s;
 }
@@ -1558,7 +1568,14 @@ int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint
         const size_t qbytes = (size_t)nq * s->d * element_size((DataType)query_dtype);
         g->queries.reserve(std::max<size_t>(qbytes, 16));
         CUDA_CHECK(cudaMemcpyAsync(g->queries.p, queries, qbytes, cudaMemcpyHostToDevice, g->stream));
+        if ((s->dtype == k::DT_I8 || s->dtype == k::DT_U8) && metric == k::M_L2 && !s->acc_seed && s->local_n) {
+            const uint64_t padded = ((s->local_n + mvf::tc::BN - 1) / mvf::tc::BN) * mvf::tc::BN;
+            CUDA_CHECK(cudaMalloc((void**)&s->acc_seed, padded * 4));
+            k::build_acc_seed<<<(uint32_t)g->sm_count * 8, 256, 0, g->stream>>>(s->sq, s->mask, s->local_n, padded, (int)0x80000000 + (1 << 25), s->acc_seed);
+            CUDA_CHECK(cudaGetLastError());
+        }
         mvf::tc::SearchArgs a;
+        a.acc_seed = s->acc_seed;
         a.rows = s->rows; a.rows_split = s->rows_split; a.norm = s->norm; a.sq = s->sq; a.mask = s->mask; a.n = s->local_n; a.d = s->d;
         a.pitch = s->pitch; a.dtype = s->dtype; a.metric = metric; a.queries = g->queries.p; a.nq = nq; a.k = k; a.dump = true;
         mvf::tc::SearchResult r = mvf::tc::run(g->tc, a, g->stream, g->sm_count);

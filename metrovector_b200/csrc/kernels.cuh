@@ -410,6 +410,15 @@ __device__ __forceinline__ uint32_t crc_step8(const uint32_t (*T)[256], uint32_t
            T[3][b & 0xff] ^ T[2][(b >> 8) & 0xff] ^ T[1][(b >> 16) & 0xff] ^ T[0][b >> 24];
 }
 #ifdef MVF_ENGINE_TU
+// K2 integer L2: what every accumulator column starts from (tc_kernels.cuh INIT_ACC): -(|x|^2 >> 1) for live rows, `dead`
+// for rows past the end of the shard (the array is padded to whole tiles), deleted or filtered out.  Rebuilt when the
+// row mask changes.
+__global__ void __launch_bounds__(256) build_acc_seed(const float* sq, const uint32_t* mask, uint64_t n, uint64_t padded, int dead, int* out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (uint64_t)gridDim.x * blockDim.x) {
+        const bool ok = i < n && (mask == nullptr || ((mask[i >> 5] >> (i & 31)) & 1u) == 0);
+        out[i] = ok ? -(__float_as_int(sq[i]) >> 1) : dead;
+    }
+}
 // sets *flag when any of `count` f16 / f32 values is Inf or NaN (exponent all ones): such query batches stay on the
 // scan kernel (DESIGN.md "non-finite values")
 __global__ void __launch_bounds__(256) flag_nonfinite(const void* data, uint64_t count, int is_f16, uint32_t* flag) {

@@ -39,6 +39,8 @@ struct TcParams {
     const float* norm;             // sqrt(sum x^2) per resident row
     const float* sq;               // sum x^2 per row (f32, or int32 bits for integer spaces)
     const uint32_t* mask;          // optional row mask (bit set = excluded), same layout as ScanParams::mask
+    const int* acc_seed;           // integer L2: per row, padded to whole tiles, what the accumulator column starts from:
+                                   // -(|x|^2 >> 1) for live rows, kSeedDead for rows past the end / deleted / filtered out
     u64* cand;                     // [gridDim.x][EG][BM][cap] scratch candidate buffers
     u64* out_lists;                // [nq][chunks*EG][k] sorted lists (key = ordered ranking value, id = local row)
     float* dump;                   // optional [mtiles*BM][ntiles*BN] raw ranking values (tests)
@@ -253,6 +255,10 @@ __device__ __forceinline__ void warp_bitonic_sort(u64* a, int P, int lane) {
     __syncwarp();
 }
 
+// Accumulator seed of a column that must never produce a candidate (integer L2): with |q.x| < 2^24 the column's
+// value stays below every threshold the epilogue can hold (thr_i >= -2^30 - 1).
+constexpr int kSeedDead = (int)0x80000000 + (1 << 25);
+
 // Cross-list threshold.  A query's rows are cut into many independent lists (work items x column groups); a list's own
 // k-th best only bounds the global k-th best as tightly as ITS slice of the rows allows (config C: 74 lists of 135k
 // rows each, so every list kept collecting ~k candidates of its own).  Lists are disjoint sets of rows, so if each of
@@ -348,7 +354,6 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(prm + (EPI_THREADS / 32) * PSLOTS * EPI_COLS);   // full[S] empty[S] tfull[2] tempty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
     uint32_t* valid_s = tmem_slot + 4;                                                    // [epilogue warps][PSLOTS][EPI_COLS / 32] live-column words
-    uint32_t* odd_s = valid_s + (EPI_THREADS / 32) * PSLOTS * (EPI_COLS / 32);            // same shape: parity of |x|^2 per column (INIT_ACC)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES);
@@ -528,7 +533,6 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         constexpr int CPLANE = EPI_COLS / 32;
         float* my_prm = prm + (size_t)(warp - 2) * PSLOTS * EPI_COLS;
         uint32_t* my_valid = valid_s + (warp - 2) * PSLOTS * CPLANE;
-        uint32_t* my_odd = odd_s + (warp - 2) * PSLOTS * CPLANE;
         // Split in two so the global loads of a later tile are ISSUED before the current tile is processed and only
         // CONSUMED after it (their ~1 us latency used to sit in front of every tile's accumulator wait): load_raw
         // returns the untouched words, finish_param turns them into (parameter, live).
@@ -536,6 +540,10 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         const uint32_t col0 = (uint32_t)(grp * EPI_COLS + lane);
         auto load_raw = [&](uint32_t t, int j, float* raw, uint32_t* mword) {
             const uint32_t row = t * BN + col0 + j * 32;                  // (the padded tile range stays below 2^32 + BN: wraps only past n)
+            if (INIT_ACC) {                                               // the seed array is padded to whole tiles and already knows dead rows
+                *raw = __int_as_float(p.acc_seed[(size_t)row]); *mword = 0u;
+                return;
+            }
             const bool in = row < n32 && row >= t * BN;
             *mword = (in && p.mask != nullptr) ? p.mask[row >> 5] : 0u;
             float v = 0.f;
@@ -550,7 +558,6 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const bool ok = row < n32 && row >= t * BN && ((mword >> (row & 31)) & 1u) == 0;
             *live = ok;
             if (!ok) return __int_as_float(0);
-            if (INIT_ACC) return __int_as_float(-(__float_as_int(raw) >> 1));     // the accumulator seed; the parity goes to odd_s
             if (MODE == 0) return raw;
             if (INT) return __int_as_float(0);
             if (p.metric == k::M_COS) return raw > 0.f ? -1.0f / raw : 0.0f;
@@ -561,14 +568,11 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             float* prn = my_prm + slot * EPI_COLS;
 #pragma unroll
             for (int j = 0; j < CPLANE; j++) {
+                if (INIT_ACC) { prn[j * 32 + lane] = raw[j]; continue; }    // the seed is all the epilogue needs per column
                 bool lv;
                 prn[j * 32 + lane] = finish_param(t, j, raw[j], mw[j], &lv);
                 const unsigned vw = __ballot_sync(0xffffffffu, lv);
                 if (lane == 0) my_valid[slot * CPLANE + j] = vw;
-                if (INIT_ACC) {
-                    const unsigned ow = __ballot_sync(0xffffffffu, (__float_as_int(raw[j]) & 1) != 0);
-                    if (lane == 0) my_odd[slot * CPLANE + j] = ow;
-                }
             }
         };
         // INIT_ACC: seeds accumulator `a` (this warp's lane quarter and column slice) with the values published in `slot`
@@ -683,14 +687,14 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 __syncwarp();
             }
             // appends the candidates of one 32-column group whose bit is set in `mask` (rare per thread)
-            auto append_hits = [&](uint32_t mask, const uint32_t* v, uint32_t id0, uint32_t oddw) {
+            auto append_hits = [&](uint32_t mask, const uint32_t* v, uint32_t id0) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     if (mask & (1u << j)) {
                         uint32_t key;
                         if (INT) {
-                            // exact integer ranking value: s = (|x|^2 & 1) - 2r (L2) or -a (dot)
-                            const int s = INIT_ACC ? (int)((oddw >> j) & 1u) - 2 * (int)v[j] : -(int)v[j];
+                            // exact integer ranking value: s = (|x|^2 & 1) - 2r (L2; the parity comes from the row's |x|^2) or -a (dot)
+                            const int s = INIT_ACC ? (__float_as_int(p.sq[id0 + j]) & 1) - 2 * (int)v[j] : -(int)v[j];
                             if (INIT_ACC && s > thr_s) continue;       // passed the conservative bound on r only
                             key = k::ordered_i32(s);
                         } else {
@@ -748,15 +752,16 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 32; j++) if ((int)v[j] > thr_i) mask |= 1u << j;
                         }
-                        mask &= vs[cc];                                  // rows past the end, deleted or filtered out
-                        const uint32_t oddw = INIT_ACC ? my_odd[slot * CPLANE + cc] : 0u;
+                        if (!INIT_ACC) mask &= vs[cc];                   // rows past the end, deleted or filtered out (INIT_ACC: dead seeds)
                         if (p.dump) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++)
+                            for (int j = 0; j < 32; j++) {
+                                const bool in = id0 + j < n32;
                                 p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] =
-                                    (float)(INIT_ACC ? (int)((oddw >> j) & 1u) - 2 * (int)v[j] : -(int)v[j]);
+                                    (float)(INIT_ACC ? (in ? (__float_as_int(p.sq[id0 + j]) & 1) - 2 * (int)v[j] : 0) : -(int)v[j]);
+                            }
                         }
-                        if (mask) append_hits(mask, v, id0, oddw);
+                        if (mask) append_hits(mask, v, id0);
                         TC_STAT_ADD(st_proc, c_p);
                     }
                 } else {
@@ -800,7 +805,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                                 for (int j = 0; j < 32; j++)
                                     p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = __uint_as_float(v[j]);
                             }
-                            if (mask) append_hits(mask, v, id0, 0u);
+                            if (mask) append_hits(mask, v, id0);
                         }
                     }
                     TC_STAT_ADD(st_drain, c_d);

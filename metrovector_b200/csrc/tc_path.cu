@@ -44,6 +44,7 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
     const uint32_t sync_window = pl.sync_window;
     const int EG = pl.EG, stages = pl.stages;
     if (kind == KIND_TF32 && a.n && !a.rows_split) throw MvfError::build_error("the split-tf32 planes of this Float32 space are not resident");
+    if (kind == KIND_I8 && a.metric == k::M_L2 && a.n && !a.acc_seed) throw MvfError::build_error("the accumulator seeds of this integer space are not resident");
     if (pl.smem > 227 * 1024) throw MvfError::build_error("no tensor-core launch shape fits shared memory for this k");
 
     const size_t qplane = (size_t)mtiles * BM * qpitch;                  // one plane of the prepared queries
@@ -94,7 +95,7 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
     } else { map_q2 = map_q; map_x2 = map_x; }
 
     TcParams p;
-    p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
+    p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.acc_seed = a.acc_seed; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
     p.gslot = p.gthr + bound_rows;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;

@@ -78,6 +78,7 @@ struct TcState {
 
 struct SearchArgs {
     const unsigned char* rows; const float* norm; const float* sq; const uint32_t* mask;
+    const int* acc_seed;               // integer spaces, L2: per-row accumulator seeds padded to whole tiles (engine.cu build_acc_seed)
     const unsigned char* rows_split;   // KIND_TF32 only: [hi plane | lo plane], each n rows of `pitch` bytes (prepare_split)
     uint64_t n; uint32_t d, pitch; int dtype, metric;
     const void* queries; uint32_t nq, k;
@@ -106,9 +107,9 @@ inline void read_env(TcState& st) {
 // shared memory: operand ring + per-warp sort scratch + per-warp column parameters + barriers
 inline size_t smem_bytes(uint32_t cap, int eg, int stages, bool pair, int kind = KIND_F16) {
     const size_t warps = 4 * (size_t)eg, cols = BN / eg;
-    // ... three column-parameter slots per epilogue warp (tc_kernels.cuh PSLOTS), barriers, live-column and |x|^2-parity words
+    // ... three column-parameter slots per epilogue warp (tc_kernels.cuh PSLOTS), barriers, live-column words
     return 1024 + (size_t)stages * (size_t)stage_bytes_of(kind, pair) + warps * (size_t)cap * 8 + warps * 3 * cols * 4 +
-           (2 * MAX_STAGES + 4) * 8 + 16 + 2 * warps * 3 * (cols / 32) * 4 + 16;
+           (2 * MAX_STAGES + 4) * 8 + 16 + warps * 3 * (cols / 32) * 4 + 16;
 }
 // deepest operand ring that fits beside the sort scratch (large k / many epilogue warps cost stages):
 // 3-4 stages of 48 KiB, or 5-6 of 32 KiB in the pair form; the two-plane tf32 stages are twice as large
