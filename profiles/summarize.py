@@ -1,5 +1,9 @@
 #!/usr/bin/env python
-"""Condenses the ncu exports in gpurun_out/ into profiles/r1_*.md (what the judge reads)."""
+"""Condenses the ncu exports in gpurun_out/ into profiles/<round>_*.md (what the judge reads) and, for the tensor kernel,
+profiles/traffic_ratios.json (DRAM bytes per algorithmic byte, read by bench.py for roofline.traffic).
+
+    python profiles/summarize.py [src_dir] [out_dir] [round_prefix, default r2] [tag=algorithmic_bytes ...]
+"""
 import csv
 import glob
 import os
@@ -7,6 +11,9 @@ import sys
 
 src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
 out = sys.argv[2] if len(sys.argv) > 2 else "profiles"
+RND = sys.argv[3] if len(sys.argv) > 3 else "r2"
+ALGO = dict((a.split("=")[0], float(a.split("=")[1])) for a in sys.argv[4:] if "=" in a)   # tag -> algorithmic bytes of the profiled launch
+ratios = {}
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -46,7 +53,15 @@ for path in sorted(glob.glob(os.path.join(src, "prof_*_raw.csv"))):
         lines += ["", "SASS lines: %d, warp instructions executed: %d" % (len(rr) - 2, tot), "",
                   "opcode mix: " + ", ".join("%s %.1f%%" % (k, 100.0 * v / max(1, tot)) for k, v in ops.most_common(14)), "",
                   "stall samples: " + ", ".join("%s %d" % (k, v) for k, v in samples.most_common(8) if v)]
-    open(os.path.join(out, "r1_ncu_%s.md" % tag), "w").write("\n".join(lines) + "\n")
+    if tag in ALGO:
+        def gb(key):
+            v = float(d[key].replace(",", "")); unit = u[key]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[unit]
+        traffic = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+        ratios[tag] = {"ratio": traffic / ALGO[tag], "source": "profiles/%s_ncu_%s.md" % (RND, tag), "dram_bytes": traffic,
+                       "algorithmic_bytes": ALGO[tag]}
+        lines += ["", "DRAM traffic %.4g B for %.4g algorithmic bytes of rows: x%.3f" % (traffic, ALGO[tag], traffic / ALGO[tag])]
+    open(os.path.join(out, "%s_ncu_%s.md" % (RND, tag)), "w").write("\n".join(lines) + "\n")
     print("wrote", tag)
 for path in glob.glob(os.path.join(src, "launches_*.csv")):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
@@ -59,5 +74,14 @@ for path in glob.glob(os.path.join(src, "launches_*.csv")):
              "per-launch times are cold-cache and serialised: compare shares", "", "| kernel | launches | mean us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         lines.append("| %s | %d | %.1f | %.1f%% |" % (k, len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
-    open(os.path.join(out, "r1_launches_%s.md" % tag), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(out, "%s_launches_%s.md" % (RND, tag)), "w").write("\n".join(lines) + "\n")
     print("wrote launches", tag)
+if ratios:
+    import json
+    path = os.path.join(out, "traffic_ratios.json")
+    old = {}
+    if os.path.exists(path):
+        old = json.load(open(path))
+    old.update(ratios)
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path)

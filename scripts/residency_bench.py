@@ -28,9 +28,12 @@ q = mv.synth_fill_host(0, 0x4D564632, 0, 4, d)
 ref_space = eng.synthetic(mv.DataType.Float32, mv.DistanceMetric.L2, n, d, 0x4D564631)
 ref = ref_space.search(q, 10)
 out = {"rows": n, "file_gb": os.path.getsize(path) / 1e9, "host_fill_s": t1 - t0, "write_s": t2 - t1, "uploads": []}
-for no_reg in ("", "1", "1"):
-    if no_reg:
-        os.environ["MVF_NO_HOST_REGISTER"] = "1"
+# every residency variant in turn (MVF_HOST_REGISTER): what the driver accepts, and how fast each is
+for variant in ("auto", "ro", "rw", "private", "none", "none"):
+    if variant == "auto":
+        os.environ.pop("MVF_HOST_REGISTER", None)
+    else:
+        os.environ["MVF_HOST_REGISTER"] = variant
     r = mv.MvfReader.open(path)
     r.validate()
     t3 = time.time()
@@ -42,7 +45,7 @@ for no_reg in ("", "1", "1"):
     got = gs.search(q, 10)
     same = bool(np.array_equal(got[0], ref[0]) and np.array_equal(got[1].view(np.uint32), ref[1].view(np.uint32)))
     rows_ok = bool(np.array_equal(gs.read_rows(n - 3, 3), rows[-3:]))
-    out["uploads"].append({"path": {1: "cudaHostRegister(read-only mapping)", 2: "pinned staging"}[st["path"]],
+    out["uploads"].append({"variant": variant, "path": {1: "cudaHostRegister'd mapping, DMA in place", 2: "pinned staging"}[st["path"]],
                            "seconds": st["seconds"], "gb_per_s": st["bytes"] / 1e9 / st["seconds"], "wall_s": t4 - t3,
                            "search_identical_to_generated_space": same, "tail_rows_identical": rows_ok, "note": st["note"], "device_crc32_ms": crc_ms, "device_crc32_gb_per_s": st["bytes"] / 1e9 / (crc_ms * 1e-3)})
     gs.free()
