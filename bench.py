@@ -199,7 +199,8 @@ def run_reference(args, rank, world):
         "config": {"workload": describe(args.workload, n, d, dt, metric, k, batch), "rows_per_gpu": n // max(1, world),
                    "parallelism": "host CPU, %d threads (the reference itself is single-threaded)" % threads,
                    "l2_policy": "sample per step (%.2f GiB) exceeds every cache" % (sample * d * ES[dt] / 2 ** 30),
-                   "path": "cpu", "step": "one query over %d of the %d rows; value = 1 / (median step x %d / %d)" % (sample, n, n, sample)},
+                   "path": "cpu"},
+        "step_definition": "one query over %d of the %d rows; value = 1 / (median step x %d / %d)" % (sample, n, n, sample),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample_txt,
                          "rows_timed": sample, "extrapolated": sample < n, "faithful_1thread": faithful},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
