@@ -260,7 +260,9 @@ bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, ui
     k::ScanTail tail;
     tail.counter = nullptr;
     bool fused = false;
-    if (fuse && !g->no_fused_merge) {
+    // (the last CTA merges the NQ queries one after the other, k outputs each, while the rest of the chip is done: only
+    // worth it while that tail is short -- otherwise K3 gets its own launch and one CTA per query)
+    if (fuse && !g->no_fused_merge && (uint32_t)NQ * p.k <= 128) {
         auto merge_smem = [&](uint32_t lists) { return ((size_t)lists + k::kScanWarps) * p.k * 8 + 16; };
         size_t smem_f = std::max(smem, merge_smem(grid));
         if (smem_f <= 96 * 1024) {

@@ -44,6 +44,12 @@ def test_plan_invariants_over_the_accepted_problem_space(dtype, es):
     ns = (1, 255, 256, 257, 4096, 100_000, 10_000_000, 100_000_000, (1 << 32) - 1)
     ds = (1, 16, 64, 96, 128, 129, 256, 300, 768, 2048, 4096)
     for nq, k, n, d in itertools.product(nqs, ks, ns, ds):
+        if dtype == 0 and d > 1024:
+            # split tf32: the tensor core's f32 accumulation over 3 d / 8 MMA steps eats the stated tolerance beyond ~1k
+            # components (DESIGN.md section 4, K2'): longer Float32 rows stay on the scan kernel
+            with pytest.raises(mv.Build):
+                mv.tc_plan(dtype, nq, k, n, d)
+            continue
         if dtype == 0 and nq <= 128 and k > 56:
             # one query tile of a Float32 space runs single CTAs with 96 KiB stages: no room for the 512-entry sort
             # scratch, the planner refuses and the engine keeps such searches on the scan kernel
