@@ -2,7 +2,10 @@
 // against the C ABI (include/mvf_b200.h) only -- exactly what a foreign-language binding sees.
 //
 //   g++ -std=c++17 -Iinclude examples/similarity_search.cpp -Lmetrovector_b200 -lmvf_b200 \
-//       -Wl,-rpath,$PWD/metrovector_b200 -o similarity_search && ./similarity_search
+//       -Wl,-rpath,$PWD/metrovector_b200 -o similarity_search && ./similarity_search [n_gpus]
+//
+// With an argument > 1 the same program drives that many GPUs from this one process (mvf_gpu_init_multi: the
+// space is row-sharded over the devices, every search uses all of them); nothing else in the program changes.
 //
 // Same dataset (three clusters of 20 vectors, examples/similarity_search.rs:43-76), same queries
 // (:103-108), k = 5 (:116).  Prints the k NEAREST vectors per query (the documented intent; the
@@ -18,7 +21,8 @@ static void check(int rc, const char* what) {
     if (rc != MVF_OK) { std::fprintf(stderr, "%s failed (%d): %s\n", what, rc, mvf_last_error()); std::exit(1); }
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const int n_gpus = argc > 1 ? std::atoi(argv[1]) : 1;
     std::printf("=== MVF Similarity Search Example (B200) ===\n\n");
     std::vector<float> vectors;
     const float centers[3][4] = {{1, 1, 1, 1}, {5, 5, 5, 5}, {-2, 3, 0, 4}};
@@ -47,7 +51,13 @@ int main() {
     mvf_space* space = nullptr;
     check(mvf_file_vector_space(file, name, &space), "vector_space");
     mvf_gpu* gpu = nullptr;
-    check(mvf_gpu_init(0, &gpu), "mvf_gpu_init");
+    if (n_gpus > 1) {
+        std::vector<int> devices(n_gpus);
+        for (int i = 0; i < n_gpus; i++) devices[i] = i;
+        check(mvf_gpu_init_multi(devices.data(), n_gpus, &gpu), "mvf_gpu_init_multi");
+    } else {
+        check(mvf_gpu_init(0, &gpu), "mvf_gpu_init");
+    }
     mvf_gpu_space* resident = nullptr;
     check(mvf_gpu_space_upload(gpu, space, &resident), "mvf_gpu_space_upload");
 

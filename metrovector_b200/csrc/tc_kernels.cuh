@@ -579,7 +579,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         [[maybe_unused]] auto seed_accumulator = [&](uint32_t a, uint32_t slot) {
             const uint4* pi = reinterpret_cast<const uint4*>(my_prm + slot * EPI_COLS);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + grp * EPI_COLS;
-#pragma unroll 1                                                    // (unrolled, ptxas hoists the loads of every piece: the tile's values + 64 seeds live -> spills)
+#pragma unroll 1                                                    // (unrolled even by two, ptxas hoists the loads: tile values + 32-64 seeds live -> spills)
             for (int c = 0; c < EPI_COLS / 16; c++) {
                 uint32_t sv[16];
 #pragma unroll
@@ -616,6 +616,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             *t = a;
             return true;
         };
+        const bool dump = p.dump != nullptr;                            // tests only
         uint32_t acc = 0, acc_phase = 0;
         [[maybe_unused]] uint32_t seq_i = 0, seq_total = 0;             // running tile number / tiles of this CTA
         [[maybe_unused]] uint32_t seq_slot = 0;                         // seq_i % 3, kept incrementally
@@ -753,7 +754,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             for (int j = 0; j < 32; j++) if ((int)v[j] > thr_i) mask |= 1u << j;
                         }
                         if (!INIT_ACC) mask &= vs[cc];                   // rows past the end, deleted or filtered out (INIT_ACC: dead seeds)
-                        if (p.dump) {
+                        if (dump) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) {
                                 const bool in = id0 + j < n32;
@@ -772,6 +773,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
                         for (int hh = 0; hh < LDG; hh++) tmem_ld32(taddr + c2 * (32 * LDG) + hh * 32, vv[hh]);
                         tmem_wait_ld();
+                        // the tile's last columns are in registers: the accumulator goes back to the issuer before they are looked at
+                        if (c2 == EPI_COLS / (32 * LDG) - 1) release_accumulator(acc);
 #pragma unroll
                         for (int hh = 0; hh < LDG; hh++) {
                             uint32_t (&v)[32] = vv[hh];
@@ -800,7 +803,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                                 for (int j = 0; j < 32; j++) if (__uint_as_float(v[j]) <= thr_f) mask |= 1u << j;
                             }
                             mask &= vs[cc];                              // rows past the end, deleted or filtered out
-                            if (p.dump) {
+                            if (dump) {
 #pragma unroll
                                 for (int j = 0; j < 32; j++)
                                     p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] = __uint_as_float(v[j]);
@@ -809,7 +812,6 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         }
                     }
                     TC_STAT_ADD(st_drain, c_d);
-                    release_accumulator(acc);
                 }
                 // A buffer past its trigger level is compacted now, by the whole warp -- after the accumulator went back to
                 // the issuer, so the sort overlaps the next tiles' MMAs instead of holding up every other warp's tile.
