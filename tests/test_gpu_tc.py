@@ -152,3 +152,60 @@ def test_every_kernel_form_matches_oracle(env, monkeypatch):
             gs.free()
     finally:
         eng.shutdown()
+
+
+def test_randomised_shapes_on_the_tensor_path(engine):
+    # seeded sweep over what the fixed cases above do not pin: ragged dimensions (K blocks partly out of bounds), row
+    # counts around tile boundaries, query counts around tile boundaries, every k class, a row mask (integer L2: folded
+    # into the accumulator seeds; other kinds: live-column words), every kind x metric -- each against the oracle
+    rng = np.random.default_rng(20261018)
+    engine.set_path(2)
+    try:
+        for case in range(36):
+            dtype = [oracle.F16, oracle.U8, oracle.I8, oracle.F32][case % 4]
+            d = int(rng.choice([8, 24, 40, 64, 100, 128, 136, 200, 256, 260, 384]))
+            n = int(rng.choice([1, 255, 256, 257, 511, 1000, 4097, 9999, 20000]))
+            nq = int(rng.choice([1, 5, 127, 128, 129, 200, 256, 257]))
+            k = int(rng.choice([1, 7, 10, 32, 33, 56]))
+            db = mv.synth_fill_host(dtype, 1000 + case, 0, n, d)
+            if case % 3 == 0 and n > 40:                                  # duplicate rows: exact ties across tiles
+                db[n // 2:n // 2 + 20] = db[:20]
+            gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
+            excluded = None
+            if case % 2 == 1 and n > 10:
+                excluded = rng.random(n) < 0.3
+                gs.set_row_mask(excluded)
+            q = mv.synth_fill_host(dtype, 2000 + case, 0, nq, d)
+            if n > 3:
+                q[0] = db[3]
+            metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
+            for metric in metrics:
+                ids, sc, isc = gs.search(q, k, metric=metric)
+                assert engine.profile_read()["last_path"] == 2, (case, dtype, n, d, nq, k)
+                qq = q.astype(np.float32) if dtype == oracle.F16 else q
+                sel = sorted(set([0, nq // 2, nq - 1]))
+                if excluded is None:
+                    check_batch(db, dtype, metric, qq[sel], k, ids[sel], sc[sel], isc[sel])
+                else:
+                    keep = np.flatnonzero(~excluded)
+                    for qi in sel:
+                        # the masked search must equal the oracle on the kept rows, reported with their original positions
+                        o_ids, o_sc, o_isc = oracle.topk(db[keep], dtype, metric, qq[qi], min(k + 8, len(keep)))
+                        got = ids[qi][ids[qi] != np.uint64(0xFFFFFFFFFFFFFFFF)].astype(np.int64)
+                        assert not excluded[got].any(), (case, metric, qi)
+                        kk = min(k, len(keep))
+                        assert len(got) == kk
+                        if dtype in (oracle.I8, oracle.U8):
+                            assert np.array_equal(got, keep[o_ids[:kk].astype(np.int64)]), (case, metric, qi, got, keep[o_ids[:kk].astype(np.int64)])
+                            assert np.array_equal(isc[qi][:kk], o_isc[:kk])
+                        else:
+                            if metric == oracle.L2:          # the tolerance is stated on d^2 (tests/util.py); near d = 0 the root amplifies it
+                                qn2 = float((qq[qi].astype(np.float64) ** 2).sum())
+                                xn2 = (db[got].astype(np.float64) ** 2).sum(1)
+                                assert (np.abs(sc[qi][:kk].astype(np.float64) ** 2 - o_sc[:kk].astype(np.float64) ** 2)
+                                        <= 2e-5 * (qn2 + xn2) + 1e-12).all(), (case, metric, qi, sc[qi][:kk], o_sc[:kk])
+                            else:
+                                assert np.allclose(sc[qi][:kk], o_sc[:kk], rtol=2e-4, atol=3e-5), (case, metric, qi)
+            gs.free()
+    finally:
+        engine.set_path(0)
