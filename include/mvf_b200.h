@@ -287,6 +287,12 @@ MVF_API int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dty
  * grid, K blocks, candidate buffer entries, compaction trigger, pacing window, epilogue warpgroups, ring stages,
  * pair form (0/1), dynamic shared memory bytes }.  Lets the CPU test-suite check the planner's invariants. */
 MVF_API int mvf_tc_plan(int data_type, uint32_t nq, uint32_t k, uint64_t n, uint32_t dimension, int sm_count, uint32_t* out16);
+/* Host arithmetic only (no GPU needed): the row count every rank of a space sharded by mvf_shard_range(global_n, world)
+ * takes the scan-vs-tensor decision on (the smallest non-empty shard: identical on every rank by construction, so the
+ * ranks never exchange candidates in two key encodings) and whether a batch of nq queries of the space's dtype would
+ * go to the tensor path in auto mode.  Lets the CPU test-suite pin the rule. */
+MVF_API int mvf_path_decision(uint64_t global_n, int world, int data_type, int metric, uint32_t nq, uint32_t k,
+                              uint32_t dimension, uint64_t* decision_rows, int* tensor_path);
 /* path selection: 0 auto, 1 bandwidth scan (K1), 2 tensor-core contraction (K2) */
 MVF_API int mvf_gpu_set_path(mvf_gpu* g, int path);
 /* instrumentation: when enabled, searches bracket the dominant kernel with CUDA events on the

@@ -124,6 +124,7 @@ _SIGS = {
     "mvf_gpu_init_multi": [_c.POINTER(_INT), _INT, _c.POINTER(_P)],
     "mvf_gpu_device_count": [_P, _c.POINTER(_INT)],
     "mvf_gpu_space_path_facts": [_P, _c.POINTER(_U64), _c.POINTER(_INT), _c.POINTER(_U64)],
+    "mvf_path_decision": [_U64, _INT, _INT, _INT, _U32, _U32, _U32, _c.POINTER(_U64), _c.POINTER(_INT)],
     "mvf_gpu_set_stream": [_P, _P],
     "mvf_gpu_device_info": [_P, _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_INT), _c.POINTER(_U64), _c.POINTER(_U64)],
     "mvf_gpu_comm_unique_id": [_P],
@@ -175,6 +176,14 @@ def tc_plan(data_type, nq, k, n, dimension, sm_count=148):
     out = (_c.c_uint32 * 16)()
     _check(_lib.mvf_tc_plan(int(data_type), nq, k, n, dimension, sm_count, out))
     return dict(zip(TC_PLAN_FIELDS, [int(v) for v in out]))
+
+
+def path_decision(global_n, world, data_type, metric, nq, k, dimension):
+    """(rows the scan-vs-tensor decision is taken on, would-take-the-tensor-path) for a space sharded over `world` ranks;
+    host arithmetic only."""
+    rows, tp = _U64(), _INT()
+    _check(_lib.mvf_path_decision(global_n, world, int(data_type), int(metric), nq, k, dimension, _c.byref(rows), _c.byref(tp)))
+    return rows.value, bool(tp.value)
 
 
 def filter_range_bitmap(column, data_type, lo, hi):

@@ -363,13 +363,17 @@ void validate_query(const mvf_gpu_space* s, int qdtype, uint32_t nq, uint32_t k,
 // number -- the smallest non-empty shard -- from (global_n, world); a rank's own row count differs between ranks
 // (the tail shard is short or empty) and must not decide: the ranks exchange packed candidates whose keys are the
 // tensor kernel's raw ranking values on one path and final keys on the other.
+uint64_t smallest_nonempty_shard(uint64_t global_n, int world) {
+    if (world < 1) world = 1;
+    const uint64_t per = (global_n + (uint64_t)world - 1) / (uint64_t)world;
+    if (per == 0) return 0;
+    const uint64_t tail = global_n % per;
+    return tail ? tail : per;
+}
 uint64_t decision_rows(const mvf_gpu_space* s) {
     const mvf_gpu* g = s->g;
     if (!(s->ranged && g->world > 1)) return s->local_n;
-    const uint64_t per = (s->global_n + (uint64_t)g->world - 1) / (uint64_t)g->world;
-    if (per == 0) return 0;
-    const uint64_t tail = s->global_n % per;
-    return tail ? tail : per;
+    return smallest_nonempty_shard(s->global_n, g->world);
 }
 bool host_queries_finite(const void* q, int qdtype, size_t count) {
     if (qdtype == k::DT_F16) {
@@ -1608,6 +1612,23 @@ int mvf_tc_plan(int data_type, uint32_t nq, uint32_t k, uint64_t n, uint32_t dim
                                 pl.cap, pl.trigger, pl.sync_window, (uint32_t)pl.EG, (uint32_t)pl.stages, pl.pair ? 1u : 0u,
                                 (uint32_t)pl.smem};
         for (int i = 0; i < 16; i++) out16[i] = v[i];
+    });
+}
+
+// Host arithmetic only (no GPU needed): the row count every rank of a space sharded by mvf_shard_range(global_n, world)
+// takes the scan-vs-tensor decision on -- the smallest non-empty shard -- and whether a batch of nq queries / top-k of
+// that dtype and metric would then go to the tensor path in auto mode (default thresholds; non-finite data aside).
+int mvf_path_decision(uint64_t global_n, int world, int data_type, int metric, uint32_t nq, uint32_t k, uint32_t dimension,
+                      uint64_t* decision_rows_out, int* tensor_path) {
+    return guard([&] {
+        if (world < 1) throw MvfError::build_error("world must be >= 1");
+        const uint64_t rows = world > 1 ? smallest_nonempty_shard(global_n, world) : global_n;
+        if (decision_rows_out) *decision_rows_out = rows;
+        if (tensor_path) {
+            mvf::tc::TcState st;
+            mvf::tc::read_env(st);
+            *tensor_path = mvf::tc::eligible(st, 0, data_type, data_type, metric, nq, k, rows, dimension, 0) ? 1 : 0;
+        }
     });
 }
 

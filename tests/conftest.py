@@ -16,7 +16,7 @@ def pytest_configure(config):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True)
     # the product library must already be built (__graft_entry__.build()); build it if the tree is fresh
     if not os.path.exists(os.path.join(ROOT, "metrovector_b200", "libmvf_b200.so")):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "metrovector_b200", "csrc")], check=True)
+        subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "metrovector_b200", "csrc")], check=True)
 
 
 @pytest.fixture(scope="session")

@@ -100,3 +100,28 @@ def test_shard_ranges_partition_the_rows():
             assert covered == n
     with pytest.raises(mv.Build):
         mv.shard_range(10, 2, 2)
+
+
+def test_every_rank_takes_the_same_scan_or_tensor_decision():
+    # the choice used to be made from a rank's own row count; with n = world * 4096 - 1 rank 0 (4096
+    # rows) took the tensor path and the tail rank (4095) the scan, and the ranks exchanged keys in two encodings.  The rule
+    # now: decide on the smallest non-empty shard of mvf_shard_range -- a function of (global_n, world) only.
+    import metrovector_b200 as mv
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, world - 1, world, world * 4096 - 1, world * 4096, world * 4096 + 1, 100_000_000, 999_999_937):
+            if n < 0:
+                continue
+            rows, _ = mv.path_decision(n, world, 1, 2, 64, 10, 768)
+            shards = [mv.shard_range(n, world, r)[1] for r in range(world)]
+            nonempty = [c for c in shards if c]
+            assert rows == (min(nonempty) if nonempty else 0), (world, n, rows, shards)
+    # Float16, 8 queries: 4096 rows per rank qualify, a 4095-row tail shard takes every rank to the scan kernel
+    assert mv.path_decision(2 * 4096, 2, 1, 2, 8, 10, 64) == (4096, True)
+    assert mv.path_decision(2 * 4096 - 1, 2, 1, 2, 8, 10, 64) == (4095, False)
+    assert mv.path_decision(8 * 4096 - 1, 8, 3, 0, 16, 10, 128) == (4095, False)
+    # what the tensor path does not take in auto mode: small batches, k > 128, integer cosine, Float32 rows beyond 1024 components
+    assert mv.path_decision(10**8, 8, 1, 2, 3, 10, 768)[1] is False
+    assert mv.path_decision(10**8, 8, 1, 2, 1024, 129, 768)[1] is False
+    assert mv.path_decision(10**8, 8, 3, 2, 1024, 10, 128)[1] is False
+    assert mv.path_decision(10**6, 1, 0, 0, 1024, 10, 768)[1] is True
+    assert mv.path_decision(10**6, 1, 0, 0, 1024, 10, 2048)[1] is False
