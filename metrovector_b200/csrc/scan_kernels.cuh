@@ -99,6 +99,37 @@ __device__ __forceinline__ void accum_float(const float* xf, const float* qf, fl
 }
 
 // CTA epilogue shared by both scan shapes: sort each query's kScanWarps*k candidates, emit best k
+// ascending bitonic sort of one 64-bit word per lane, in registers
+__device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const u64 o = shfl_xor_u64(v, stride);
+            const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+            v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+        }
+    }
+    return v;
+}
+// k <= 32 (register lists): every warp sorts its own list with shuffles, then warp q merges the kScanWarps sorted lists
+// of query q by tournament straight into the CTA's output list: two block barriers instead of the 28 of a 128-word
+// block sort (the fixed cost of a search is what the small configs pay: a 256-row scan took 12.5 us).
+template <int NQ>
+__device__ __forceinline__ void emit_cta_lists_reg(const ScanParams& p, u64* lists, const u64 (&regl)[NQ], int lane, int warp) {
+    const int k = (int)p.k;
+    __syncthreads();                                            // everybody is done with the query area / lists
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        const u64 v = warp_sort32(lane < k ? regl[q] : kInf, lane);
+        if (lane < k) lists[(size_t)q * p.P + warp * k + lane] = v;
+    }
+    __syncthreads();
+    for (int q = warp; q < NQ; q += kScanWarps) {
+        u64* out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
+        warp_tournament(lists + (size_t)q * p.P, (size_t)k, (uint32_t)kScanWarps, p.k, out, lane);
+    }
+}
 template <int NQ>
 __device__ __forceinline__ void emit_cta_lists(const ScanParams& p, u64* lists) {
     __syncthreads();
@@ -183,17 +214,17 @@ template <int R, int LPR> struct RowsLeft { static constexpr int CNT = (R / LPR)
 // offer the candidates held by the lanes of a warp (kInf = nothing) to the warp's running list
 // k <= 32: the warp's running list lives in registers, one entry per lane (lanes >= k hold 0 and never
 // are the maximum); an insert overwrites the lane holding the current maximum and re-reduces (max, lane).
+// (max, lane) of the 64-bit entries comes from two hardware warp reductions (REDUX) on the halves and one ballot
+// instead of a five-round shuffle butterfly: inserts are what a short scan is made of (config A: ~24 per warp for 42 rows).
 __device__ __forceinline__ void reg_list_insert(u64& mine, int k, u64 cand, u64& thr, int& pos, int lane) {
     if (lane == pos) mine = cand;
-    u64 m = lane < k ? mine : 0ull;
-    int mp = lane;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const u64 om = shfl_xor_u64(m, off);
-        const int op = __shfl_xor_sync(0xffffffffu, mp, off);
-        if (om > m || (om == m && op < mp)) { m = om; mp = op; }
-    }
-    thr = m; pos = mp;
+    const bool real = lane < k;
+    const uint32_t hi = real ? (uint32_t)(mine >> 32) : 0u, lo = real ? (uint32_t)mine : 0u;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const unsigned who = __ballot_sync(0xffffffffu, real && hi == mh && lo == ml);   // equal entries (kInf fillers): lowest lane
+    thr = ((u64)mh << 32) | ml;
+    pos = __ffs(who) - 1;
 }
 __device__ __forceinline__ void offer(u64 pk, u64* list, int k, u64& thr, int& pos, int lane, u64& mine, bool regmode) {
     unsigned hits = __ballot_sync(0xffffffffu, pk < thr);
@@ -365,11 +396,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
     }
     };
     if (ragged) run(std::true_type{}); else run(std::false_type{});
-    if (regmode) {
-#pragma unroll
-        for (int q = 0; q < NQ; q++) if (lane < (int)p.k) lists[(size_t)q * p.P + warp * p.k + lane] = regl[q];
-    }
-    emit_cta_lists<NQ>(p, lists);
+    if (regmode) emit_cta_lists_reg<NQ>(p, lists, regl, lane, warp);
+    else emit_cta_lists<NQ>(p, lists);
     fused_merge_tail<NQ>(p, tail, smem);
 }
 
@@ -506,10 +534,9 @@ __device__ __forceinline__ void narrow_body(const ScanParams& p, u64* lists, con
         if (g >= groups) break;
         step(y, x);
     }
-    if (regmode) {
-#pragma unroll
-        for (int q = 0; q < NQ; q++) if (lane < (int)p.k) lists[(size_t)q * p.P + warp * p.k + lane] = regl[q];
-    }
+    // CTA epilogue (all threads of the CTA run the same narrow_body instantiation)
+    if (regmode) emit_cta_lists_reg<NQ>(p, lists, regl, lane, warp);
+    else emit_cta_lists<NQ>(p, lists);
 }
 
 template <int DT, int OP, int NQ, int R>
@@ -532,7 +559,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_narrow(const ScanPa
         case 8: narrow_body<DT, OP, NQ, R, 8>(p, lists, q_s, dpad, qc_s); break;
         default: narrow_body<DT, OP, NQ, R, 16>(p, lists, q_s, dpad, qc_s); break;
     }
-    emit_cta_lists<NQ>(p, lists);
     fused_merge_tail<NQ>(p, tail, smem);
 }
 
