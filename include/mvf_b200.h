@@ -178,8 +178,9 @@ MVF_API int mvf_builder_save(mvf_builder* b, const char* path);
 MVF_API int mvf_gpu_init(int device, mvf_gpu** out);
 /* ONE process, n devices: the engine behind a single call site of find_top_k_similar (examples/similarity_search.rs:117)
  * that uses every GPU of the box.  Spaces created on it are row-sharded over the devices (mvf_shard_range), a search
- * runs the shards' kernels concurrently, exchanges the local top-k with one ncclAllGather per device (communicator
- * from ncclCommInitAll) and merges on devices[0].  n = 1 gives a plain single-device engine.  mvf_gpu_set_stream,
+ * runs the shards' kernels concurrently, exchanges the local top-k (peer stores into devices[0]'s window for small
+ * payloads, else one ncclAllGather per device on the communicator from ncclCommInitAll; see mvf_gpu_exchange_info)
+ * and merges on devices[0].  n = 1 gives a plain single-device engine.  mvf_gpu_set_stream,
  * mvf_gpu_comm_init and mvf_gpu_tc_dump are single-device calls and answer MVF_ERR_BUILD on such an engine;
  * mvf_gpu_search_device takes pointers into devices[0]'s memory. */
 MVF_API int mvf_gpu_init_multi(const int* devices, int n, mvf_gpu** out);
@@ -301,6 +302,15 @@ MVF_API int mvf_gpu_profile(mvf_gpu* g, int enable);
 MVF_API int mvf_gpu_profile_read(mvf_gpu* g, double* scan_ms_total, uint64_t* scan_launches,
                                  uint64_t* all_launches, int* last_path);
 MVF_API int mvf_gpu_synchronize(mvf_gpu* g);
+/* The one exchange step of a sharded search (every rank contributes its nq*k best, merged per query; replaces nothing
+ * in the reference, which is single-threaded: examples/similarity_search.rs:147) runs in one of two ways, the same on
+ * every rank: payloads of up to 512 candidates (every batch-1 search) are pushed into every rank's window with peer
+ * stores over NVLink and merged by the same kernel (windows shared by cudaIpc* between processes, by peer access inside
+ * a one-process engine); larger ones use ncclAllGather + the merge kernel.  *peer_ready = 1 when the peer path is set up
+ * (decided collectively at mvf_gpu_comm_init / mvf_gpu_init_multi; MVF_PEER_EXCHANGE=0 turns it off), the counters say
+ * which route the searches of this engine took, mvf_gpu_exchange_note why the peer path is off when it is. */
+MVF_API int mvf_gpu_exchange_info(const mvf_gpu* g, int* peer_ready, uint64_t* peer_searches, uint64_t* nccl_searches);
+MVF_API const char* mvf_gpu_exchange_note(const mvf_gpu* g);
 
 /* host helpers shared by callers that move candidates themselves (and by the tests) */
 MVF_API uint32_t mvf_ordered_key_f32(float v);

@@ -160,6 +160,7 @@ _SIGS = {
     "mvf_gpu_profile": [_P, _INT],
     "mvf_gpu_profile_read": [_P, _c.POINTER(_c.c_double), _c.POINTER(_U64), _c.POINTER(_U64), _c.POINTER(_INT)],
     "mvf_gpu_synchronize": [_P],
+    "mvf_gpu_exchange_info": [_P, _c.POINTER(_INT), _c.POINTER(_U64), _c.POINTER(_U64)],
     "mvf_synth_fill_host": [_P, _INT, _U64, _U64, _U64, _U32],
 }
 for _name, _args in _SIGS.items():
@@ -541,6 +542,16 @@ class GpuEngine:
 
     def synchronize(self):
         _check(_lib.mvf_gpu_synchronize(self._h))
+
+    def exchange_info(self):
+        """How sharded searches exchange their candidates: peer-memory kernel set up?, searches per route, note."""
+        ready, ps, ns = _INT(), _U64(), _U64()
+        _check(_lib.mvf_gpu_exchange_info(self._h, _c.byref(ready), _c.byref(ps), _c.byref(ns)))
+        _lib.mvf_gpu_exchange_note.restype = _c.c_char_p
+        _lib.mvf_gpu_exchange_note.argtypes = [_P]
+        note = _lib.mvf_gpu_exchange_note(self._h)
+        return dict(peer_ready=bool(ready.value), peer_searches=ps.value, nccl_searches=ns.value,
+                    note=(note or b"").decode())
 
     def upload(self, space):
         h = _P()

@@ -128,6 +128,19 @@ struct mvf_gpu {
     uint32_t* pinned_flag = nullptr;       // mapped pinned word the device writes "this query batch holds Inf/NaN" into
     uint32_t* pinned_flag_dev = nullptr;
     cudaEvent_t xdev_event = nullptr;      // group engines: orders a member's stream against another member's
+    // X1, the exchange over peer memory (kernels.cuh exchange_merge): this rank's window, every rank's window as mapped
+    // into this device, and the search counter that selects buffer and flag.  `ready` is agreed by all ranks at set-up.
+    struct PeerExchange {
+        bool ready = false, ipc = false;
+        unsigned char* window = nullptr;
+        std::vector<unsigned char*> peer;      // [world]
+        DevBuf peer_table;                     // the same pointers on the device
+        uint64_t seq = 0;                      // peer-exchange searches so far (identical on every rank)
+        uint32_t* error = nullptr;             // mapped pinned word the kernel raises when a peer's cells never arrive
+        uint32_t* error_dev = nullptr;
+        std::string note;                      // why the peer path is off, if it is
+    } px;
+    uint64_t peer_searches = 0, nccl_searches = 0;
     mvf::tc::TcState tc;
     // one stream + one set of scratch buffers per engine: every entry point that touches them takes this lock, so
     // calls from several host threads are serialised instead of racing (SURVEY.md 8b "Threading")
@@ -518,7 +531,7 @@ void search_exchange(mvf_gpu_space* s, const SearchCtx& ctx) {
     const size_t cnt = (size_t)ctx.nq * ctx.kk;
     g->gathered.reserve(cnt * 8 * (size_t)g->world);
     nccl_check(nccl().AllGather(ctx.packed_local, g->gathered.p, cnt, kNcclUint64, g->comm, g->stream), "ncclAllGather");
-    g->all_launches++;
+    g->all_launches++; g->nccl_searches++;
 }
 
 // Phase 3: merge of the W gathered lists per query; identical on every rank that runs it.
@@ -535,11 +548,172 @@ void search_final(mvf_gpu_space* s, const SearchCtx& ctx, uint64_t* d_ids, float
     launch_merge(g, mp, ctx.nq);
 }
 
+
+// ---- X1: exchange over peer memory ---------------------------------------------------------------------
+// Small payloads (nq * k <= kPeerSlotCells words: every batch-1 search) skip NCCL: the local merge's nq*k words are
+// pushed into every rank's window and merged there by ONE kernel (kernels.cuh exchange_merge) -- the collective and
+// the merge that follows it are the same launch.  Large batches keep ncclAllGather (bandwidth, not latency).
+constexpr uint32_t kPeerSlotCells = 512;                     // 16-byte cells per (buffer, rank) slot: 8 KiB
+size_t peer_window_bytes(int world) { return (size_t)2 * (size_t)world * kPeerSlotCells * 16; }
+
+bool peer_exchange_wanted() {
+    const char* e = std::getenv("MVF_PEER_EXCHANGE");
+    return !(e && *e == '0');
+}
+void peer_exchange_release(mvf_gpu* g) {
+    auto& px = g->px;
+    if (px.ipc) for (int r = 0; r < (int)px.peer.size(); r++) if (r != g->rank && px.peer[(size_t)r]) cudaIpcCloseMemHandle(px.peer[(size_t)r]);
+    px.peer.clear();
+    if (px.window) cudaFree(px.window);
+    px.window = nullptr;
+    px.peer_table.release();
+    if (px.error) cudaFreeHost(px.error);
+    px.error = nullptr; px.error_dev = nullptr;
+    px.ready = false;
+}
+// this rank's window (zeroed: flag 0 is never used) and the error word
+void peer_exchange_alloc(mvf_gpu* g) {
+    auto& px = g->px;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    CUDA_CHECK(cudaMalloc((void**)&px.window, peer_window_bytes(g->world)));
+    CUDA_CHECK(cudaMemset(px.window, 0, peer_window_bytes(g->world)));
+    CUDA_CHECK(cudaHostAlloc((void**)&px.error, 64, cudaHostAllocMapped));
+    *px.error = 0;
+    CUDA_CHECK(cudaHostGetDevicePointer((void**)&px.error_dev, px.error, 0));
+    CUDA_CHECK(cudaDeviceSynchronize());
+}
+void peer_exchange_publish_table(mvf_gpu* g) {
+    auto& px = g->px;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    px.peer_table.reserve(sizeof(void*) * px.peer.size());
+    CUDA_CHECK(cudaMemcpy(px.peer_table.p, px.peer.data(), sizeof(void*) * px.peer.size(), cudaMemcpyHostToDevice));
+}
+// One process per GPU: windows are shared with cudaIpc handles, carried to the other ranks by the communicator that
+// was just created.  Collective; every rank ends with the same `ready` (all-gathered), so the ranks of a search always
+// take the same exchange.
+void peer_exchange_setup_ipc(mvf_gpu* g) {
+    auto& px = g->px;
+    const int W = g->world;
+    uint64_t ok = 1;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    // (a rank that does not want the peer path still takes part in the two rounds below: set-up is collective)
+    if (!peer_exchange_wanted()) { ok = 0; px.note = "MVF_PEER_EXCHANGE=0"; }
+    else if (W > 128) { ok = 0; px.note = "more than 128 ranks"; }
+    if (ok) { try { peer_exchange_alloc(g); } catch (const MvfError& e) { ok = 0; px.note = e.what(); cudaGetLastError(); } }
+    if (ok && cudaIpcGetMemHandle(&mine, px.window) != cudaSuccess) { ok = 0; px.note = "cudaIpcGetMemHandle refused"; cudaGetLastError(); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    // round 1: handle + "I could export"; round 2: "I could map everybody"
+    const size_t rec = 72;
+    g->scalar_tmp.reserve(rec + rec * (size_t)W + 8 + 8 * (size_t)W);
+    unsigned char* base = (unsigned char*)g->scalar_tmp.p;
+    std::vector<unsigned char> sendrec(rec), all(rec * (size_t)W);
+    std::memcpy(sendrec.data(), &mine, 64); std::memcpy(sendrec.data() + 64, &ok, 8);
+    CUDA_CHECK(cudaMemcpyAsync(base, sendrec.data(), rec, cudaMemcpyHostToDevice, g->stream));
+    nccl_check(nccl().AllGather(base, base + rec, rec / 8, kNcclUint64, g->comm, g->stream), "ncclAllGather");
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), base + rec, rec * (size_t)W, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    uint64_t everyone = 1;
+    for (int r = 0; r < W; r++) { uint64_t o; std::memcpy(&o, all.data() + rec * (size_t)r + 64, 8); everyone &= o; }
+    uint64_t mapped = everyone;
+    if (everyone) {
+        px.peer.assign((size_t)W, nullptr);
+        px.peer[(size_t)g->rank] = px.window;
+        px.ipc = true;
+        for (int r = 0; r < W && mapped; r++) {
+            if (r == g->rank) continue;
+            cudaIpcMemHandle_t h; std::memcpy(&h, all.data() + rec * (size_t)r, 64);
+            void* ptr = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { mapped = 0; px.note = std::string("cudaIpcOpenMemHandle refused: ") + cudaGetErrorName(e); cudaGetLastError(); }
+            else px.peer[(size_t)r] = (unsigned char*)ptr;
+        }
+    } else if (px.note.empty()) px.note = "a peer could not export its window";
+    unsigned char* base2 = base + rec + rec * (size_t)W;
+    std::vector<uint64_t> all2((size_t)W);
+    CUDA_CHECK(cudaMemcpyAsync(base2, &mapped, 8, cudaMemcpyHostToDevice, g->stream));
+    nccl_check(nccl().AllGather(base2, base2 + 8, 1, kNcclUint64, g->comm, g->stream), "ncclAllGather");
+    CUDA_CHECK(cudaMemcpyAsync(all2.data(), base2 + 8, 8 * (size_t)W, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    uint64_t all_mapped = 1;
+    for (uint64_t v : all2) all_mapped &= v;
+    if (!all_mapped) { if (px.note.empty()) px.note = "a peer could not map the windows"; peer_exchange_release(g); return; }
+    peer_exchange_publish_table(g);
+    px.ready = true;
+}
+// One process, G devices: plain peer access between the members' devices.
+void peer_exchange_setup_group(mvf_gpu* grp) {
+    const size_t G = grp->members.size();
+    auto off = [&](const std::string& why) { for (mvf_gpu* m : grp->members) { peer_exchange_release(m); m->px.note = why; } };
+    if (!peer_exchange_wanted()) { off("MVF_PEER_EXCHANGE=0"); return; }
+    if (G > 128) { off("more than 128 devices"); return; }
+    for (size_t i = 0; i < G; i++)
+        for (size_t j = 0; j < G; j++) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, grp->members[i]->device, grp->members[j]->device) != cudaSuccess || !can) {
+                cudaGetLastError(); off("devices without peer access"); return;
+            }
+        }
+    try {
+        for (size_t i = 0; i < G; i++) {
+            CUDA_CHECK(cudaSetDevice(grp->members[i]->device));
+            for (size_t j = 0; j < G; j++) {
+                if (i == j) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(grp->members[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+                cudaGetLastError();
+            }
+            peer_exchange_alloc(grp->members[i]);
+        }
+        for (size_t i = 0; i < G; i++) {
+            auto& px = grp->members[i]->px;
+            px.peer.assign(G, nullptr);
+            for (size_t j = 0; j < G; j++) px.peer[j] = grp->members[j]->px.window;
+            peer_exchange_publish_table(grp->members[i]);
+            px.ready = true;
+        }
+    } catch (const MvfError& e) { cudaGetLastError(); off(e.what()); }
+}
+bool peer_exchange_fits(const mvf_gpu* g, const SearchCtx& ctx) {
+    if (!g->px.ready || !ctx.multi) return false;
+    const size_t cnt = (size_t)ctx.nq * ctx.kk;
+    return cnt <= kPeerSlotCells && ((size_t)g->world + 1) * ctx.kk * 8 <= 48 * 1024;
+}
+// Phases 2 + 3 as one launch.  do_merge = false: push and wait only (group members whose result nobody reads).
+void search_exchange_peer(mvf_gpu_space* s, const SearchCtx& ctx, bool do_merge, uint64_t* d_ids, float* d_scores, int32_t* d_iscores) {
+    mvf_gpu* g = s->g;
+    auto& px = g->px;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    k::ExchangeParams x;
+    x.mine = ctx.packed_local; x.peers = (uint4* const*)px.peer_table.p; x.window = (uint4*)px.window;
+    x.world = (uint32_t)g->world; x.rank = (uint32_t)g->rank; x.slot_cells = kPeerSlotCells;
+    x.buf = (uint32_t)(px.seq & 1); x.flag = (uint32_t)((px.seq >> 1) % 0xfffffffeull) + 1u;
+    x.error = px.error_dev; x.do_merge = do_merge ? 1 : 0;
+    px.seq++;
+    k::MergeParams mp;
+    mp.in = nullptr; mp.q_stride = 0; mp.list_stride = 0; mp.nlists = (uint32_t)g->world; mp.k = ctx.kk; mp.P = 0; mp.seg_lists = 0;
+    mp.id_add = 0; mp.metric = ctx.metric; mp.dtype = s->dtype; mp.tc_mode = ctx.tc_keys ? 1 : 0; mp.qconst = ctx.tc_qconst;
+    mp.out_packed = nullptr; mp.out_ids = d_ids; mp.out_scores = d_scores; mp.out_iscores = d_iscores;
+    mp.ext_ids = s->ext_ids;
+    const size_t smem = ((size_t)g->world + 1) * ctx.kk * 8;
+    k::exchange_merge<<<ctx.nq, 128, smem, g->stream>>>(x, mp);
+    CUDA_CHECK(cudaGetLastError());
+    g->all_launches++; g->peer_searches++;
+}
+void peer_exchange_check(mvf_gpu* g) {                       // after a stream sync: did a kernel give up on a peer?
+    if (g->px.error && *(volatile uint32_t*)g->px.error) {
+        *g->px.error = 0;
+        throw MvfError::nccl("peer exchange timed out: a rank of the communicator did not deliver its candidates");
+    }
+}
+
 // Full search of a single-device space with device-resident queries/outputs.
 void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t nq, uint32_t kk, int metric, int qfinite,
                    uint64_t* d_ids, float* d_scores, int32_t* d_iscores) {
     SearchCtx ctx;
     search_local(s, d_queries, qdtype, nq, kk, metric, qfinite, d_ids, d_scores, d_iscores, &ctx);
+    if (peer_exchange_fits(s->g, ctx)) { search_exchange_peer(s, ctx, true, d_ids, d_scores, d_iscores); return; }
     search_exchange(s, ctx);
     search_final(s, ctx, d_ids, d_scores, d_iscores);
 }
@@ -894,6 +1068,7 @@ void destroy_engine(mvf_gpu* g) {
         g->out_ids.release(); g->out_scores.release(); g->out_iscores.release(); g->merge_tmp[0].release(); g->merge_tmp[1].release();
         g->gather_ids.release(); g->gather_out.release(); g->crc_tables.release(); g->scalar_tmp.release(); g->scan_counter.release();
         mvf::tc::release(g->tc);
+        peer_exchange_release(g);
         if (g->pinned_out) cudaFreeHost(g->pinned_out);
         if (g->pinned_flag) cudaFreeHost(g->pinned_flag);
         if (g->xdev_event) cudaEventDestroy(g->xdev_event);
@@ -1103,6 +1278,7 @@ void search_host(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_
         search_device(s, g->queries.p, query_dtype, nq, k, metric, qfinite, (uint64_t*)dev, (float*)(dev + cnt * 8),
                       out_iscores ? (int32_t*)(dev + cnt * 12) : nullptr);
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        peer_exchange_check(g);
         std::memcpy(out_ids, g->pinned_out, cnt * 8);
         if (out_scores) std::memcpy(out_scores, g->pinned_out + cnt * 8, cnt * 4);
         if (out_iscores) std::memcpy(out_iscores, g->pinned_out + cnt * 12, cnt * 4);
@@ -1117,6 +1293,7 @@ void search_host(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_
         if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, d_scores, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
         if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, d_isc, cnt * 4, cudaMemcpyDeviceToHost, g->stream));
         CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        peer_exchange_check(g);
     }
 }
 
@@ -1163,13 +1340,25 @@ void search_group(mvf_gpu_space* S, const void* queries, bool on_device, int que
         }
         search_local(sh, dq, query_dtype, nq, k, metric, qfinite, nullptr, nullptr, nullptr, &ctx[i]);
     }
-    nccl_check(nccl().GroupStart(), "ncclGroupStart");
-    for (size_t i = 0; i < G; i++) search_exchange(S->shards[i], ctx[i]);
-    nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+    // small payloads: every member pushes its candidates into every member's window (peer stores) and member 0 merges
+    // what arrived in its own -- one launch per device, no NCCL; the other members wait for the same cells so that
+    // nobody runs two searches ahead of a reader (kernels.cuh exchange_merge)
+    const bool peer = peer_exchange_fits(g0, ctx[0]);
+    if (peer) {
+        for (size_t i = 1; i < G; i++) search_exchange_peer(S->shards[i], ctx[i], false, nullptr, nullptr, nullptr);
+    } else {
+        nccl_check(nccl().GroupStart(), "ncclGroupStart");
+        for (size_t i = 0; i < G; i++) search_exchange(S->shards[i], ctx[i]);
+        nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+    }
     CUDA_CHECK(cudaSetDevice(g0->device));
+    auto final_merge = [&](uint64_t* ids, float* scores, int32_t* iscores) {
+        if (peer) search_exchange_peer(S->shards[0], ctx[0], true, ids, scores, iscores);
+        else search_final(S->shards[0], ctx[0], ids, scores, iscores);
+    };
     if (on_device) {
         for (size_t i = 1; i < G; i++) CUDA_CHECK(cudaStreamWaitEvent(g0->stream, S->shards[i]->g->xdev_event, 0));
-        search_final(S->shards[0], ctx[0], out_ids, out_scores, out_iscores);
+        final_merge(out_ids, out_scores, out_iscores);
         return;                                                             // asynchronous on member 0's stream
     }
     g0->out_ids.reserve(cnt * 16);
@@ -1177,11 +1366,12 @@ void search_group(mvf_gpu_space* S, const void* queries, bool on_device, int que
     uint64_t* d_ids = (uint64_t*)dev;
     float* d_scores = (float*)(dev + cnt * 8);
     int32_t* d_isc = (int32_t*)(dev + cnt * 12);
-    search_final(S->shards[0], ctx[0], d_ids, d_scores, out_iscores ? d_isc : nullptr);
+    final_merge(d_ids, d_scores, out_iscores ? d_isc : nullptr);
     CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids, cnt * 8, cudaMemcpyDeviceToHost, g0->stream));
     if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, d_scores, cnt * 4, cudaMemcpyDeviceToHost, g0->stream));
     if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, d_isc, cnt * 4, cudaMemcpyDeviceToHost, g0->stream));
     CUDA_CHECK(cudaStreamSynchronize(g0->stream));
+    peer_exchange_check(g0);
 }
 
 void require_single(const mvf_gpu* g, const char* what) {
@@ -1222,6 +1412,7 @@ int mvf_gpu_init_multi(const int* devices, int n, mvf_gpu** out) {
         std::vector<NcclComm> comms((size_t)n, nullptr);
         nccl_check(nccl().CommInitAll(comms.data(), n, devices), "ncclCommInitAll");
         for (int i = 0; i < n; i++) grp->members[(size_t)i]->comm = comms[(size_t)i];
+        peer_exchange_setup_group(grp.get());
         *out = grp.release();
     });
 }
@@ -1279,6 +1470,7 @@ int mvf_gpu_comm_init(mvf_gpu* g, const void* unique_id_128_bytes, int rank, int
         if (world == 1) return;
         NcclUniqueId id; std::memcpy(&id, unique_id_128_bytes, 128);
         nccl_check(nccl().CommInitRank(&g->comm, world, id, rank), "ncclCommInitRank");
+        peer_exchange_setup_ipc(g);
     });
 }
 
@@ -1673,9 +1865,25 @@ int mvf_gpu_profile_read(mvf_gpu* g, double* scan_ms_total, uint64_t* scan_launc
 
 int mvf_gpu_synchronize(mvf_gpu* g) {
     return guard([&] { EngineLock engine_lock(g->mu);
-        auto one = [&](mvf_gpu* e) { CUDA_CHECK(cudaSetDevice(e->device)); CUDA_CHECK(cudaStreamSynchronize(e->stream)); };
+        auto one = [&](mvf_gpu* e) { CUDA_CHECK(cudaSetDevice(e->device)); CUDA_CHECK(cudaStreamSynchronize(e->stream)); peer_exchange_check(e); };
         if (g->is_group()) for (mvf_gpu* m : g->members) one(m); else one(g);
     });
+}
+
+// How the exchange step of sharded searches runs on this engine: *peer_ready = 1 when small payloads go through the
+// peer-memory kernel (X1), the searches that took each route so far, and (when the peer path is off) why.
+int mvf_gpu_exchange_info(const mvf_gpu* g, int* peer_ready, uint64_t* peer_searches, uint64_t* nccl_searches) {
+    return guard([&] {
+        const mvf_gpu* e = g->is_group() ? g->members[0] : g;
+        if (peer_ready) *peer_ready = e->px.ready ? 1 : 0;
+        if (peer_searches) *peer_searches = e->peer_searches;
+        if (nccl_searches) *nccl_searches = e->nccl_searches;
+    });
+}
+const char* mvf_gpu_exchange_note(const mvf_gpu* g) {
+    if (!g) return "";
+    const mvf_gpu* e = g->is_group() ? g->members[0] : g;
+    return e->px.note.c_str();
 }
 
 }  // extern "C"

@@ -338,6 +338,69 @@ __global__ void __launch_bounds__(256) merge_topk_warp(const MergeParams p, uint
         }
     }
 }
+// ------------------------------------------------------------------------------------------------
+// X1 -- exchange_merge: the cross-GPU step of a sharded search as ONE kernel over peer memory (NVLink / NVSwitch
+// loads and stores), instead of ncclAllGather + K3.  Every rank owns a window other ranks can write
+// (cudaIpc* between processes, peer access inside one process): [2 buffers][world ranks][slot_cells] cells of 16
+// bytes {lo32, flag, hi32, flag}.  CTA q pushes this rank's k candidates of query q into slot `rank` of EVERY
+// rank's window, data and flag in the same 16-byte store (each 8-byte half carries its own copy of the flag, the
+// way NCCL's LL protocol does, so no fence and no separate flag round trip is needed), then polls its own window
+// until the k cells of every rank carry this search's flag, and merges the `world` sorted lists.  Two buffers
+// alternate: a rank can start pushing search e+1 only after its own merge of search e, and it can finish the merge of
+// e+1 only after everybody pushed e+1, so nobody is ever two searches ahead of a reader.
+// ------------------------------------------------------------------------------------------------
+struct ExchangeParams {
+    const u64* mine;          // [nq][k] this rank's merged candidates (global row ids already applied)
+    uint4* const* peers;      // [world] window of rank r as mapped into this device (peers[rank] = window)
+    uint4* window;            // this rank's own window
+    uint32_t world, rank;
+    uint32_t slot_cells;      // cells per (buffer, rank) slot, >= nq * k
+    uint32_t buf, flag;       // buffer of this search (0/1) and its flag value (never 0, differs between consecutive uses of a buffer)
+    uint32_t* error;          // mapped pinned word: set when a peer's cells did not arrive within the time limit
+    int do_merge;             // 0: push and wait only (members of a one-process group other than the first)
+};
+__device__ __forceinline__ void st_cell(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cell(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+__global__ void __launch_bounds__(128) exchange_merge(const ExchangeParams x, const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    u64* cand = reinterpret_cast<u64*>(smem);               // [world][k], then [k] merged
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, k = p.k, W = x.world;
+    const size_t slot0 = (size_t)x.buf * W * x.slot_cells;
+    // push: my k words of query q into slot `rank` of every rank's window
+    for (uint32_t i = tid; i < W * k; i += blockDim.x) {
+        const uint32_t r = i / k, j = i - r * k;
+        const u64 w = x.mine[(size_t)q * k + j];
+        st_cell(x.peers[r] + slot0 + (size_t)x.rank * x.slot_cells + (size_t)q * k + j,
+                make_uint4((uint32_t)w, x.flag, (uint32_t)(w >> 32), x.flag));
+    }
+    // gather: every rank's k words of query q from my own window
+    const unsigned long long t0 = globaltimer_ns();
+    for (uint32_t i = tid; i < W * k; i += blockDim.x) {
+        const uint32_t r = i / k, j = i - r * k;
+        const uint4* cell = x.window + slot0 + (size_t)r * x.slot_cells + (size_t)q * k + j;
+        uint4 c = ld_cell(cell);
+        while (c.y != x.flag || c.w != x.flag) {
+            if (globaltimer_ns() - t0 > 20000000000ull) { *x.error = 1u; c = make_uint4(~0u, 0, ~0u, 0); break; }   // a peer is gone: fail, do not hang
+            __nanosleep(64);
+            c = ld_cell(cell);
+        }
+        cand[(size_t)r * k + j] = ((u64)c.z << 32) | c.x;
+    }
+    __syncthreads();
+    if (!x.do_merge || tid >= 32) return;
+    u64* out = cand + (size_t)W * k;
+    warp_tournament(cand, k, W, k, out, (int)tid);
+    for (uint32_t j = tid; j < k; j += 32) emit_result(p, q, j, out[j]);
+}
 #endif  // MVF_ENGINE_TU
 
 // ------------------------------------------------------------------------------------------------

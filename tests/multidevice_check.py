@@ -3,7 +3,7 @@
     python tests/multidevice_check.py          # needs >= 2 GPUs; prints "multidevice ok world N"
 
 The group engine row-shards every space over its devices, runs the shards' kernels concurrently, exchanges the local
-top-k with one ncclAllGather per device (ncclCommInitAll communicator) and merges on device 0.  A second, single-device
+top-k (peer stores for small payloads, else one ncclAllGather per device) and merges on device 0.  A second, single-device
 engine on GPU 0 holds the whole database for the bit-identity check.
 """
 import os
@@ -117,6 +117,38 @@ def main():
             print("MISMATCH read_rows across a shard boundary")
         gs.free()
         r.close()
+
+    # back-to-back searches with device-resident queries/results on device 0 (no host sync in between): the peer-memory
+    # exchange alternates two buffers; 300 queued searches, each compared with the single-device engine afterwards
+    n, d, k, rounds = 24000, 64, 10, 300
+    db = mv.synth_fill_host(1, 5, 0, n, d)
+    gs = eng.from_host(db, mv.DataType.Float16, mv.DistanceMetric.Cosine)
+    full = solo.from_host(db, mv.DataType.Float16, mv.DistanceMetric.Cosine)
+    qh = mv.synth_fill_host(1, 6, 0, 3 * rounds, d).astype(np.float32)
+    with torch.cuda.device(0):
+        dq = torch.from_numpy(qh).cuda()
+        d_ids = torch.zeros((rounds, 3, k), dtype=torch.int64, device="cuda")
+        d_sc = torch.zeros((rounds, 3, k), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        for i in range(rounds):
+            gs.search_device(dq[3 * i].data_ptr(), 0, 1 + i % 3, k, 2, d_ids[i].data_ptr(), d_sc[i].data_ptr())
+        eng.synchronize()
+        got_i, got_s = d_ids.cpu().numpy().view(np.uint64), d_sc.cpu().numpy()
+    ids1, sc1, _ = full.search(qh, k)
+    for i in range(rounds):
+        nq = 1 + i % 3
+        if not (np.array_equal(got_i[i, :nq], ids1[3 * i:3 * i + nq]) and
+                np.array_equal(got_s[i, :nq].view(np.uint32), sc1[3 * i:3 * i + nq].view(np.uint32))):
+            failures += 1
+            print("MISMATCH back-to-back search", i)
+            break
+    gs.free()
+    full.free()
+    info = eng.exchange_info()
+    print("exchange:", info)
+    if os.environ.get("MVF_PEER_EXCHANGE", "1") != "0" and not (info["peer_ready"] and info["peer_searches"] > rounds and info["nccl_searches"] > 0):
+        failures += 1
+        print("peer exchange not in use", info)
 
     # single-device-only calls answer Build on a group engine
     try:

@@ -4,7 +4,7 @@ Run under torchrun (one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tests/multirank_check.py
 Each rank holds its row shard (device-generated), every rank calls the same search, results are
-merged with ONE ncclAllGather of nq*k packed candidates inside the library.  Rank 0 additionally
+exchanged inside the library: nq*k packed candidates per rank, over peer memory (small payloads) or ONE ncclAllGather.  Rank 0 additionally
 holds the whole database on a second, communicator-less engine and checks bit-identity.
 """
 import os
@@ -133,6 +133,42 @@ def main():
                 failures += 1
                 print("MISMATCH external ids / mask on shards, query", qi)
     gs.free()
+    # back-to-back searches without a host sync in between (device-resident queries and results): the peer-memory
+    # exchange alternates two buffers and relies on nobody running two searches ahead of a reader -- 400 searches of
+    # 1..3 queries queued at once, every result compared with the communicator-less engine afterwards
+    n, d, k, rounds = 24000, 64, 10, 400
+    gs = eng.synthetic(mv.DataType.Float16, mv.DistanceMetric.Cosine, n, d, seed=5)
+    qh = mv.synth_fill_host(1, 6, 0, 3 * rounds, d).astype(np.float32)
+    dq = torch.from_numpy(qh).cuda()
+    d_ids = torch.zeros((rounds, 3, k), dtype=torch.int64, device="cuda")
+    d_sc = torch.zeros((rounds, 3, k), dtype=torch.float32, device="cuda")
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    for i in range(rounds):
+        nq = 1 + i % 3
+        gs.search_device(dq[3 * i].data_ptr(), 0, nq, k, 2, d_ids[i].data_ptr(), d_sc[i].data_ptr())
+    eng.synchronize()
+    torch.cuda.synchronize()
+    if rank == 0:
+        full = solo.from_host(mv.synth_fill_host(1, 5, 0, n, d), mv.DataType.Float16, mv.DistanceMetric.Cosine)
+        ids1, sc1, _ = full.search(qh, k)
+        got_i, got_s = d_ids.cpu().numpy().view(np.uint64), d_sc.cpu().numpy()
+        for i in range(rounds):
+            nq = 1 + i % 3
+            if not (np.array_equal(got_i[i, :nq], ids1[3 * i:3 * i + nq]) and
+                    np.array_equal(got_s[i, :nq].view(np.uint32), sc1[3 * i:3 * i + nq].view(np.uint32))):
+                failures += 1
+                print("MISMATCH back-to-back search", i)
+                break
+        full.free()
+    gs.free()
+    info = eng.exchange_info()
+    if rank == 0:
+        print("exchange:", info)
+    if os.environ.get("MVF_PEER_EXCHANGE", "1") != "0":
+        # both routes must have been exercised: small payloads over peer memory, large batches over NCCL
+        if not (info["peer_ready"] and info["peer_searches"] > rounds and info["nccl_searches"] > 0):
+            failures += 1
+            print("peer exchange not in use on rank", rank, info)
     dist.barrier()
     if rank == 0:
         print("multirank ok" if failures == 0 else "multirank FAILED", "world", world)
