@@ -238,7 +238,9 @@ template <int DT> size_t scan_smem(int NQ, uint32_t P, uint32_t dpad) {
     return (size_t)NQ * P * 8 + ((q_bytes + 15) & ~(size_t)15) + (size_t)NQ * sizeof(k::QueryConst) + 64;
 }
 
-bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out, k::MergeParams* fuse);
+struct FinalOut { uint64_t* ids; float* scores; int32_t* iscores; };
+bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out, k::MergeParams* fuse,
+                 const k::ExchangeParams* xchg = nullptr, const FinalOut* fin = nullptr);
 size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
     switch (dtype) {
         case k::DT_F32: return scan_smem<k::DT_F32>(NQ, P, scan_shape<k::DT_F32>(pitch).dpad);
@@ -252,7 +254,11 @@ size_t scan_smem_any(int dtype, int NQ, uint32_t P, uint32_t pitch) {
 // per-CTA lists are merged by the last CTA of the SAME launch whenever they fit its shared memory (<= 1024 lists,
 // <= 96 KiB): one launch per search instead of two -- what the latency-bound configs are made of.  Returns whether
 // the merge was fused; if not the caller launches K3.
-bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out, k::MergeParams* fuse) {
+// With `xchg` (sharded search, small payload) a fused launch also carries the exchange: the last CTA pushes the merged list
+// into every rank's window, waits for the other ranks' lists and writes the FINAL result (`fin`) -- one launch per search
+// on every GPU.
+bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, uint32_t* grid_out, k::MergeParams* fuse,
+                 const k::ExchangeParams* xchg, const FinalOut* fin) {
     ScanShape sh;
     const void* fn = nullptr;
     const int op = p.metric == k::M_L2 ? k::OP_L2 : k::OP_DOT;
@@ -272,12 +278,14 @@ bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, ui
     uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)g->sm_count * nb, want));
     k::ScanTail tail;
     tail.counter = nullptr;
+    tail.exchange = 0;
     bool fused = false;
     // (the last CTA merges the NQ queries one after the other, k outputs each, while the rest of the chip is done: only
     // worth it while that tail is short -- otherwise K3 gets its own launch and one CTA per query)
     if (fuse && !g->no_fused_merge && (uint32_t)NQ * p.k <= 128) {
         auto merge_smem = [&](uint32_t lists) { return ((size_t)lists + k::kScanWarps) * p.k * 8 + 16; };
         size_t smem_f = std::max(smem, merge_smem(grid));
+        if (xchg) smem_f = std::max(smem_f, ((size_t)xchg->world + 1 + k::kScanWarps) * p.k * 8 + 16);
         if (smem_f <= 96 * 1024) {
             int nb_f = occupancy(g, fn, k::kScanThreads, smem_f);          // a larger allocation may cost resident CTAs
             if (g->ctas_per_sm_cap > 0) nb_f = std::min(nb_f, g->ctas_per_sm_cap);
@@ -291,6 +299,10 @@ bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, ui
                 fuse->in = p.cand; fuse->q_stride = (size_t)grid * p.k; fuse->list_stride = p.k; fuse->nlists = grid;
                 tail.counter = (uint32_t*)g->scan_counter.p;
                 tail.mp = *fuse;
+                if (xchg) {
+                    tail.exchange = 1; tail.x = *xchg;
+                    tail.mp.out_packed = nullptr; tail.mp.out_ids = fin->ids; tail.mp.out_scores = fin->scores; tail.mp.out_iscores = fin->iscores;
+                }
             }
         }
     }
@@ -426,6 +438,24 @@ int device_queries_finite(mvf_gpu* g, const void* d_queries, int qdtype, size_t 
     return *(volatile uint32_t*)g->pinned_flag ? QF_NONFINITE : QF_FINITE;
 }
 
+// X1 (exchange over peer memory, set-up further down): payloads of up to kPeerSlotCells candidates
+constexpr uint32_t kPeerSlotCells = 512;                     // 16-byte cells per (buffer, rank) slot: 8 KiB
+bool peer_exchange_fits(const mvf_gpu* g, uint32_t nq, uint32_t kk) {
+    if (!g->px.ready) return false;
+    return (size_t)nq * kk <= kPeerSlotCells && ((size_t)g->world + 1) * kk * 8 <= 48 * 1024;
+}
+// buffer and flag of the next peer exchange of this engine (one per search, the same sequence on every rank)
+k::ExchangeParams next_exchange(mvf_gpu* g, bool do_merge) {
+    auto& px = g->px;
+    k::ExchangeParams x;
+    x.mine = nullptr; x.peers = (uint4* const*)px.peer_table.p; x.window = (uint4*)px.window;
+    x.world = (uint32_t)g->world; x.rank = (uint32_t)g->rank; x.slot_cells = kPeerSlotCells;
+    x.buf = (uint32_t)(px.seq & 1); x.flag = (uint32_t)((px.seq >> 1) % 0xfffffffeull) + 1u;
+    x.error = px.error_dev; x.do_merge = do_merge ? 1 : 0;
+    px.seq++;
+    return x;
+}
+
 // What one search leaves behind between its phases.
 struct SearchCtx {
     uint32_t nq = 0, kk = 0; int metric = 0;
@@ -433,13 +463,16 @@ struct SearchCtx {
     bool tc_keys = false;          // packed keys are the tensor kernel's ranking values (decoded with qconst at the final merge)
     const float* tc_qconst = nullptr;
     u64* packed_local = nullptr;
+    bool peer = false;             // the exchange goes over peer memory (X1); x holds this search's buffer and flag
+    bool exchange_done = false;    // ... and already happened inside the scan launch (K1 + K3 + X1)
+    k::ExchangeParams x;
 };
 
 // Phase 1: this shard's kernels and its local merge.  Without a communicator the local merge writes the final
 // outputs; with one it leaves nq*k packed candidates (global row ids applied) for the exchange.
 // Asynchronous on g->stream (except the finite check of device-resident float queries, see above).
 void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t nq, uint32_t kk, int metric, int qfinite,
-                  uint64_t* d_ids, float* d_scores, int32_t* d_iscores, SearchCtx* ctx) {
+                  uint64_t* d_ids, float* d_scores, int32_t* d_iscores, SearchCtx* ctx, bool final_here = true) {
     mvf_gpu* g = s->g;
     if (metric == MVF_METRIC_SPACE_DEFAULT) metric = s->metric;
     validate_query(s, qdtype, nq, kk, metric);
@@ -449,6 +482,10 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
     if (multi) { g->packed_local.reserve((size_t)nq * kk * 8); packed_local = (u64*)g->packed_local.p; }
     ctx->nq = nq; ctx->kk = kk; ctx->metric = metric; ctx->multi = multi; ctx->packed_local = packed_local;
     ctx->tc_keys = false; ctx->tc_qconst = nullptr;
+    // (final_here = false: a group member whose merged result nobody reads -- it pushes and waits only)
+    ctx->peer = multi && peer_exchange_fits(g, nq, kk);
+    ctx->exchange_done = false;
+    if (ctx->peer) ctx->x = next_exchange(g, final_here);
 
     bool use_tc = tensor_candidate(s, qdtype, nq, kk, metric);
     if (use_tc && (s->dtype == k::DT_F32 || s->dtype == k::DT_F16)) {
@@ -513,7 +550,11 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         mp.out_iscores = multi ? nullptr : (d_iscores ? d_iscores + o : nullptr);
         mp.ext_ids = s->ext_ids;
         bool fused = false;
-        if (s->local_n > 0) fused = launch_scan(g, s, p, NQ, &grid, &mp);
+        // a sharded search that is ONE scan launch carries its exchange and the final merge in that launch
+        const bool fuse_x = ctx->peer && (uint32_t)NQ == nq;
+        const FinalOut fin = {d_ids, d_scores, d_iscores};
+        if (s->local_n > 0) fused = launch_scan(g, s, p, NQ, &grid, &mp, fuse_x ? &ctx->x : nullptr, fuse_x ? &fin : nullptr);
+        if (fused && fuse_x) { ctx->exchange_done = true; g->peer_searches++; }
         if (!fused) {
             mp.q_stride = (size_t)grid * kk; mp.nlists = grid;
             launch_merge(g, mp, (uint32_t)NQ);
@@ -553,7 +594,6 @@ void search_final(mvf_gpu_space* s, const SearchCtx& ctx, uint64_t* d_ids, float
 // Small payloads (nq * k <= kPeerSlotCells words: every batch-1 search) skip NCCL: the local merge's nq*k words are
 // pushed into every rank's window and merged there by ONE kernel (kernels.cuh exchange_merge) -- the collective and
 // the merge that follows it are the same launch.  Large batches keep ncclAllGather (bandwidth, not latency).
-constexpr uint32_t kPeerSlotCells = 512;                     // 16-byte cells per (buffer, rank) slot: 8 KiB
 size_t peer_window_bytes(int world) { return (size_t)2 * (size_t)world * kPeerSlotCells * 16; }
 
 bool peer_exchange_wanted() {
@@ -675,22 +715,13 @@ void peer_exchange_setup_group(mvf_gpu* grp) {
         }
     } catch (const MvfError& e) { cudaGetLastError(); off(e.what()); }
 }
-bool peer_exchange_fits(const mvf_gpu* g, const SearchCtx& ctx) {
-    if (!g->px.ready || !ctx.multi) return false;
-    const size_t cnt = (size_t)ctx.nq * ctx.kk;
-    return cnt <= kPeerSlotCells && ((size_t)g->world + 1) * ctx.kk * 8 <= 48 * 1024;
-}
-// Phases 2 + 3 as one launch.  do_merge = false: push and wait only (group members whose result nobody reads).
-void search_exchange_peer(mvf_gpu_space* s, const SearchCtx& ctx, bool do_merge, uint64_t* d_ids, float* d_scores, int32_t* d_iscores) {
+// Phases 2 + 3 as one launch (when they did not already ride on the scan launch).
+void search_exchange_peer(mvf_gpu_space* s, const SearchCtx& ctx, uint64_t* d_ids, float* d_scores, int32_t* d_iscores) {
     mvf_gpu* g = s->g;
-    auto& px = g->px;
+    if (ctx.exchange_done) return;
     CUDA_CHECK(cudaSetDevice(g->device));
-    k::ExchangeParams x;
-    x.mine = ctx.packed_local; x.peers = (uint4* const*)px.peer_table.p; x.window = (uint4*)px.window;
-    x.world = (uint32_t)g->world; x.rank = (uint32_t)g->rank; x.slot_cells = kPeerSlotCells;
-    x.buf = (uint32_t)(px.seq & 1); x.flag = (uint32_t)((px.seq >> 1) % 0xfffffffeull) + 1u;
-    x.error = px.error_dev; x.do_merge = do_merge ? 1 : 0;
-    px.seq++;
+    k::ExchangeParams x = ctx.x;
+    x.mine = ctx.packed_local;
     k::MergeParams mp;
     mp.in = nullptr; mp.q_stride = 0; mp.list_stride = 0; mp.nlists = (uint32_t)g->world; mp.k = ctx.kk; mp.P = 0; mp.seg_lists = 0;
     mp.id_add = 0; mp.metric = ctx.metric; mp.dtype = s->dtype; mp.tc_mode = ctx.tc_keys ? 1 : 0; mp.qconst = ctx.tc_qconst;
@@ -713,7 +744,7 @@ void search_device(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t
                    uint64_t* d_ids, float* d_scores, int32_t* d_iscores) {
     SearchCtx ctx;
     search_local(s, d_queries, qdtype, nq, kk, metric, qfinite, d_ids, d_scores, d_iscores, &ctx);
-    if (peer_exchange_fits(s->g, ctx)) { search_exchange_peer(s, ctx, true, d_ids, d_scores, d_iscores); return; }
+    if (ctx.peer) { search_exchange_peer(s, ctx, d_ids, d_scores, d_iscores); return; }
     search_exchange(s, ctx);
     search_final(s, ctx, d_ids, d_scores, d_iscores);
 }
@@ -1320,6 +1351,14 @@ void search_group(mvf_gpu_space* S, const void* queries, bool on_device, int que
         if (!g0->xdev_event) CUDA_CHECK(cudaEventCreateWithFlags(&g0->xdev_event, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(g0->xdev_event, g0->stream));
     }
+    // where member 0 leaves the final result: the caller's device buffers, or a device block copied back below
+    uint64_t* f_ids = out_ids; float* f_scores = out_scores; int32_t* f_isc = out_iscores;
+    if (!on_device) {
+        CUDA_CHECK(cudaSetDevice(g0->device));
+        g0->out_ids.reserve(cnt * 16);
+        unsigned char* dev = (unsigned char*)g0->out_ids.p;
+        f_ids = (uint64_t*)dev; f_scores = (float*)(dev + cnt * 8); f_isc = out_iscores ? (int32_t*)(dev + cnt * 12) : nullptr;
+    }
     std::vector<SearchCtx> ctx(G);
     for (size_t i = 0; i < G; i++) {
         mvf_gpu_space* sh = S->shards[i];
@@ -1338,38 +1377,30 @@ void search_group(mvf_gpu_space* S, const void* queries, bool on_device, int que
             }
             dq = g->queries.p;
         }
-        search_local(sh, dq, query_dtype, nq, k, metric, qfinite, nullptr, nullptr, nullptr, &ctx[i]);
+        // (small payloads: the exchange and member 0's final merge may already ride on this launch, see search_local)
+        if (i == 0) search_local(sh, dq, query_dtype, nq, k, metric, qfinite, f_ids, f_scores, f_isc, &ctx[i], true);
+        else search_local(sh, dq, query_dtype, nq, k, metric, qfinite, nullptr, nullptr, nullptr, &ctx[i], false);
     }
     // small payloads: every member pushes its candidates into every member's window (peer stores) and member 0 merges
-    // what arrived in its own -- one launch per device, no NCCL; the other members wait for the same cells so that
-    // nobody runs two searches ahead of a reader (kernels.cuh exchange_merge)
-    const bool peer = peer_exchange_fits(g0, ctx[0]);
-    if (peer) {
-        for (size_t i = 1; i < G; i++) search_exchange_peer(S->shards[i], ctx[i], false, nullptr, nullptr, nullptr);
+    // what arrived in its own -- no NCCL; the other members wait for the same cells so that nobody runs two searches
+    // ahead of a reader (kernels.cuh exchange_merge).  Large payloads: one ncclGroup of G all-gathers, merge on member 0.
+    if (ctx[0].peer) {
+        for (size_t i = 1; i < G; i++) search_exchange_peer(S->shards[i], ctx[i], nullptr, nullptr, nullptr);
+        search_exchange_peer(S->shards[0], ctx[0], f_ids, f_scores, f_isc);
     } else {
         nccl_check(nccl().GroupStart(), "ncclGroupStart");
         for (size_t i = 0; i < G; i++) search_exchange(S->shards[i], ctx[i]);
         nccl_check(nccl().GroupEnd(), "ncclGroupEnd");
+        search_final(S->shards[0], ctx[0], f_ids, f_scores, f_isc);
     }
     CUDA_CHECK(cudaSetDevice(g0->device));
-    auto final_merge = [&](uint64_t* ids, float* scores, int32_t* iscores) {
-        if (peer) search_exchange_peer(S->shards[0], ctx[0], true, ids, scores, iscores);
-        else search_final(S->shards[0], ctx[0], ids, scores, iscores);
-    };
     if (on_device) {
         for (size_t i = 1; i < G; i++) CUDA_CHECK(cudaStreamWaitEvent(g0->stream, S->shards[i]->g->xdev_event, 0));
-        final_merge(out_ids, out_scores, out_iscores);
         return;                                                             // asynchronous on member 0's stream
     }
-    g0->out_ids.reserve(cnt * 16);
-    unsigned char* dev = (unsigned char*)g0->out_ids.p;
-    uint64_t* d_ids = (uint64_t*)dev;
-    float* d_scores = (float*)(dev + cnt * 8);
-    int32_t* d_isc = (int32_t*)(dev + cnt * 12);
-    final_merge(d_ids, d_scores, out_iscores ? d_isc : nullptr);
-    CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids, cnt * 8, cudaMemcpyDeviceToHost, g0->stream));
-    if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, d_scores, cnt * 4, cudaMemcpyDeviceToHost, g0->stream));
-    if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, d_isc, cnt * 4, cudaMemcpyDeviceToHost, g0->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out_ids, f_ids, cnt * 8, cudaMemcpyDeviceToHost, g0->stream));
+    if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, f_scores, cnt * 4, cudaMemcpyDeviceToHost, g0->stream));
+    if (out_iscores) CUDA_CHECK(cudaMemcpyAsync(out_iscores, f_isc, cnt * 4, cudaMemcpyDeviceToHost, g0->stream));
     CUDA_CHECK(cudaStreamSynchronize(g0->stream));
     peer_exchange_check(g0);
 }

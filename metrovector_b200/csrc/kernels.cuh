@@ -232,10 +232,58 @@ __device__ __forceinline__ void warp_tournament(const u64* base, size_t stride, 
     __syncwarp();
 }
 
+// X1 parameters (exchange_merge below; also the tail of a fused scan launch, scan_kernels.cuh)
+struct ExchangeParams {
+    const u64* mine;          // [nq][k] this rank's merged candidates (global row ids already applied)
+    uint4* const* peers;      // [world] window of rank r as mapped into this device (peers[rank] = window)
+    uint4* window;            // this rank's own window
+    uint32_t world, rank;
+    uint32_t slot_cells;      // cells per (buffer, rank) slot, >= nq * k
+    uint32_t buf, flag;       // buffer of this search (0/1) and its flag value (never 0, differs between consecutive uses of a buffer)
+    uint32_t* error;          // mapped pinned word: set when a peer's cells did not arrive within the time limit
+    int do_merge;             // 0: push and wait only (members of a one-process group other than the first)
+};
+__device__ __forceinline__ void st_cell(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cell(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+
+// every rank's k words of query q (cells written by exchange_push of all ranks) from this rank's window into `cand`
+// ([world][k]); polls until the cells carry this search's flag
+__device__ __forceinline__ void exchange_gather(const ExchangeParams& x, uint32_t q, uint32_t k, u64* cand, uint32_t tid, uint32_t nthreads) {
+    const size_t slot0 = (size_t)x.buf * x.world * x.slot_cells;
+    const unsigned long long t0 = globaltimer_ns();
+    for (uint32_t i = tid; i < x.world * k; i += nthreads) {
+        const uint32_t r = i / k, j = i - r * k;
+        const uint4* cell = x.window + slot0 + (size_t)r * x.slot_cells + (size_t)q * k + j;
+        uint4 c = ld_cell(cell);
+        while (c.y != x.flag || c.w != x.flag) {
+            if (globaltimer_ns() - t0 > 20000000000ull) { *x.error = 1u; c = make_uint4(~0u, 0, ~0u, 0); break; }   // a peer is gone: fail, do not hang
+            __nanosleep(64);
+            c = ld_cell(cell);
+        }
+        cand[(size_t)r * k + j] = ((u64)c.z << 32) | c.x;
+    }
+}
+// word j of query q of this rank into slot `rank` of every rank's window
+__device__ __forceinline__ void exchange_push(const ExchangeParams& x, uint32_t q, uint32_t k, uint32_t j, uint32_t r, u64 w) {
+    const size_t slot0 = (size_t)x.buf * x.world * x.slot_cells;
+    st_cell(x.peers[r] + slot0 + (size_t)x.rank * x.slot_cells + (size_t)q * k + j, make_uint4((uint32_t)w, x.flag, (uint32_t)(w >> 32), x.flag));
+}
+
 // K1 + K3 in one launch: what the scan kernels need to merge their own per-CTA lists (the last CTA to finish does it)
 struct ScanTail {
     uint32_t* counter;        // CTAs finished so far (zero between launches); nullptr = no fused merge, K3 is launched separately
     MergeParams mp;           // in / q_stride / nlists describe ScanParams::cand of the same launch
+    int exchange;             // K1 + K3 + X1 in one launch: the last CTA also pushes the merged list to every rank, waits for theirs
+    ExchangeParams x;         // and merges them (mp then describes the FINAL outputs; mp.id_add is applied before the push)
 };
 
 #ifdef MVF_ENGINE_TU   // non-template kernels: defined in engine.cu's translation unit only
@@ -349,52 +397,15 @@ __global__ void __launch_bounds__(256) merge_topk_warp(const MergeParams p, uint
 // alternate: a rank can start pushing search e+1 only after its own merge of search e, and it can finish the merge of
 // e+1 only after everybody pushed e+1, so nobody is ever two searches ahead of a reader.
 // ------------------------------------------------------------------------------------------------
-struct ExchangeParams {
-    const u64* mine;          // [nq][k] this rank's merged candidates (global row ids already applied)
-    uint4* const* peers;      // [world] window of rank r as mapped into this device (peers[rank] = window)
-    uint4* window;            // this rank's own window
-    uint32_t world, rank;
-    uint32_t slot_cells;      // cells per (buffer, rank) slot, >= nq * k
-    uint32_t buf, flag;       // buffer of this search (0/1) and its flag value (never 0, differs between consecutive uses of a buffer)
-    uint32_t* error;          // mapped pinned word: set when a peer's cells did not arrive within the time limit
-    int do_merge;             // 0: push and wait only (members of a one-process group other than the first)
-};
-__device__ __forceinline__ void st_cell(uint4* p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_cell(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
-}
 __global__ void __launch_bounds__(128) exchange_merge(const ExchangeParams x, const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     u64* cand = reinterpret_cast<u64*>(smem);               // [world][k], then [k] merged
     const uint32_t q = blockIdx.x, tid = threadIdx.x, k = p.k, W = x.world;
-    const size_t slot0 = (size_t)x.buf * W * x.slot_cells;
-    // push: my k words of query q into slot `rank` of every rank's window
     for (uint32_t i = tid; i < W * k; i += blockDim.x) {
         const uint32_t r = i / k, j = i - r * k;
-        const u64 w = x.mine[(size_t)q * k + j];
-        st_cell(x.peers[r] + slot0 + (size_t)x.rank * x.slot_cells + (size_t)q * k + j,
-                make_uint4((uint32_t)w, x.flag, (uint32_t)(w >> 32), x.flag));
+        exchange_push(x, q, k, j, r, x.mine[(size_t)q * k + j]);
     }
-    // gather: every rank's k words of query q from my own window
-    const unsigned long long t0 = globaltimer_ns();
-    for (uint32_t i = tid; i < W * k; i += blockDim.x) {
-        const uint32_t r = i / k, j = i - r * k;
-        const uint4* cell = x.window + slot0 + (size_t)r * x.slot_cells + (size_t)q * k + j;
-        uint4 c = ld_cell(cell);
-        while (c.y != x.flag || c.w != x.flag) {
-            if (globaltimer_ns() - t0 > 20000000000ull) { *x.error = 1u; c = make_uint4(~0u, 0, ~0u, 0); break; }   // a peer is gone: fail, do not hang
-            __nanosleep(64);
-            c = ld_cell(cell);
-        }
-        cand[(size_t)r * k + j] = ((u64)c.z << 32) | c.x;
-    }
+    exchange_gather(x, q, k, cand, tid, blockDim.x);
     __syncthreads();
     if (!x.do_merge || tid >= 32) return;
     u64* out = cand + (size_t)W * k;

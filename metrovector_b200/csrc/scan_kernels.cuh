@@ -171,9 +171,32 @@ __device__ __forceinline__ void fused_merge_tail(const ScanParams& p, const Scan
         __syncthreads();
         if (warp == 0) {
             warp_tournament(lvl1, k, kScanWarps, k, cand_s, (int)lane);
-            for (uint32_t j = lane; j < k; j += 32) emit_result(tail.mp, (uint32_t)q, j, cand_s[j]);
+            if (!tail.exchange) {
+                for (uint32_t j = lane; j < k; j += 32) emit_result(tail.mp, (uint32_t)q, j, cand_s[j]);
+            } else {
+                // sharded search, small payload: this rank's list goes straight into every rank's window (X1)
+                for (uint32_t j = lane; j < k; j += 32) {
+                    u64 v = cand_s[j];
+                    if (v != kInf) v += tail.mp.id_add;
+                    for (uint32_t r = 0; r < tail.x.world; r++) exchange_push(tail.x, p.q0 + (uint32_t)q, k, j, r, v);
+                }
+            }
         }
         __syncthreads();
+        if (tail.exchange) {
+            // ... and the lists of all ranks are merged here as soon as they have arrived: K1 + K3 + X1 in one launch
+            u64* xc = cand_s;                               // [world][k] + [k] (the host sized the allocation for it)
+            exchange_gather(tail.x, p.q0 + (uint32_t)q, k, xc, threadIdx.x, blockDim.x);
+            __syncthreads();
+            if (warp == 0 && tail.x.do_merge) {
+                u64* out = xc + (size_t)tail.x.world * k;
+                warp_tournament(xc, k, tail.x.world, k, out, (int)lane);
+                MergeParams fin = tail.mp;
+                fin.id_add = 0;
+                for (uint32_t j = lane; j < k; j += 32) emit_result(fin, (uint32_t)q, j, out[j]);
+            }
+            __syncthreads();
+        }
     }
 }
 
