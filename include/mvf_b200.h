@@ -268,7 +268,7 @@ MVF_API int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uin
  * fewer than 2^32 rows; a row is at most 1 MiB; integer spaces have dimension <= 33025 (int32 accumulation,
  * SURVEY.md 8a); the per-CTA candidate lists of the scan kernel live in shared memory, so k is bounded by
  * 8 * pow2(8k) + dimension * 4 (or * 1 for integer spaces) <= ~227 KB, i.e. k <= 2048 for rows up to 24 KB;
- * the tensor-core path is taken for k <= 128 only (larger k run on the scan kernel).
+ * the tensor-core path is taken for k <= 512 only (larger k run on the scan kernel).
  * Float spaces holding Inf/NaN rows, and batches holding Inf/NaN queries, always run on the scan kernel. */
 MVF_API int mvf_gpu_search(mvf_gpu_space* s, const void* queries, int query_dtype, uint32_t nq,
                            uint32_t k, int metric, uint64_t* out_ids, float* out_scores,

@@ -1822,7 +1822,7 @@ int mvf_gpu_tc_dump(mvf_gpu_space* s, const void* queries, int query_dtype, uint
 // sync_window, epilogue groups, stages, pair form (0/1), dynamic shared memory bytes.  No CUDA call is made.
 int mvf_tc_plan(int data_type, uint32_t nq, uint32_t k, uint64_t n, uint32_t dimension, int sm_count, uint32_t* out16) {
     return guard([&] {
-        if (!out16 || sm_count < 2 || nq == 0 || k == 0 || k > 128 || n == 0 || dimension == 0 || data_type < 0 || data_type > 3)
+        if (!out16 || sm_count < 2 || nq == 0 || k == 0 || k > (uint32_t)mvf::tc::MAX_K || n == 0 || dimension == 0 || data_type < 0 || data_type > 3)
             throw MvfError::build_error("no tensor-core plan for these arguments");
         mvf::tc::TcState st;
         mvf::tc::read_env(st);

@@ -24,7 +24,8 @@ constexpr int BM = 128;            // queries per tile (TMEM lanes)
 constexpr int BN = 256;            // database rows per tile (TMEM columns, MMA N)
 constexpr int BKB = 128;           // K block in bytes (one 128-byte swizzle row)
 constexpr int MAX_STAGES = 6;
-constexpr int MAX_CAP = 512;       // candidate buffer entries per query (power of two)
+constexpr int MAX_CAP = 1024;      // candidate buffer entries per query (power of two)
+constexpr int MAX_K = 512;         // largest k the fused epilogue keeps (a buffer holds k + two tiles of appends)
 constexpr int A_BYTES = BM * BKB;  // 16 KiB
 constexpr int B_BYTES = BN * BKB;  // 32 KiB
 // operand kinds.  KIND_TF32 is K2' (Float32 spaces): every operand is carried as two tf32-exact planes
@@ -129,16 +130,22 @@ inline uint32_t trigger_for_k(uint32_t k) {
     return p2 - 16;
 }
 inline uint32_t cap_for_k(uint32_t k, int eg) {
-    const uint32_t want = trigger_for_k(k) + (uint32_t)(BN / eg);
+    uint32_t want = trigger_for_k(k) + (uint32_t)(BN / eg);
+    // k > 128: a 2.5k-entry sort scratch per epilogue warp would cost the operand ring its stages; k entries plus two
+    // tiles of appends keep the scratch at 32-64 KiB per CTA (sorts of <= 1024 entries, >= one tile admitted per sort)
+    if (k > 128) want = k + 2u * (uint32_t)(BN / eg);
+    const uint32_t lim = k > 128 ? (uint32_t)MAX_CAP : 512u;
     uint32_t cap = 128;
-    while (cap < want && cap < (uint32_t)MAX_CAP) cap <<= 1;
+    while (cap < want && cap < lim) cap <<= 1;
     return cap;
 }
 
 // K2 takes f16 spaces with f16 queries, f32 spaces with f32 queries (split tf32) and int8/uint8 spaces (any metric
-// except integer cosine, whose exact definition needs a division per element), k <= 128.  `n` must be a value every
+// except integer cosine, whose exact definition needs a division per element), k <= MAX_K (512).  `n` must be a value every
 // rank of a sharded space agrees on (engine.cu passes the smallest non-empty shard): ranks on different paths would
 // exchange keys in different encodings.
+struct TcState;
+inline bool plan_fits(const TcState& st, int dtype, uint32_t nq, uint32_t k, uint64_t n, uint32_t d);   // below make_plan
 inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int metric, uint32_t nq, uint32_t k, uint64_t n,
                      uint32_t d, uint32_t pitch) {
     (void)pitch;
@@ -147,12 +154,14 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
     const bool f32 = dtype == 0 && qdtype == 0;
     const bool i8 = (dtype == 2 || dtype == 3) && qdtype == dtype && metric != 2;
     if (!(f16 || f32 || i8)) return false;
-    if (k > 128 || n == 0 || d == 0) return false;
+    if (k > (uint32_t)MAX_K || n == 0 || d == 0) return false;
     // split tf32: the tensor core's f32 accumulation over 3 * d / 8 MMA steps leaves ~4e-6 |q||x| at d = 768 (measured,
     // tests/test_gpu_tc.py); the stated tolerance is 1e-5 |q||x|, so longer rows stay on the scan kernel
     if (f32 && d > 1024) return false;
     // the single-CTA split-tf32 form (one query tile) has 96 KiB stages: two of them do not fit beside the 512-entry sort scratch
     if (f32 && (nq <= (uint32_t)BM || st.cluster == 1) && smem_bytes(cap_for_k(k, 2), 2, 2, false, KIND_TF32) > 227 * 1024) return false;
+    // (large k: the sort scratch must leave room for the operand ring in the form make_plan picks)
+    if (k > 128 && !plan_fits(st, dtype, nq, k, n, d)) return false;
     if (path == 2) return true;
     return nq >= (uint32_t)(f16 ? st.min_batch_f16 : (f32 ? st.min_batch_f32 : st.min_batch_i8)) && n >= 4096;
 }
@@ -205,6 +214,12 @@ inline Plan make_plan(const TcState& st, int dtype, uint32_t nq, uint32_t kk, ui
         pl.sync_window = (uint32_t)std::min(64.0, std::max(2.0, 16.0 * 1048576.0 / (runs * tile_bytes)));
     }
     return pl;
+}
+
+inline bool plan_fits(const TcState& st, int dtype, uint32_t nq, uint32_t k, uint64_t n, uint32_t d) {
+    const uint32_t es = elem_bytes(kind_of(dtype));
+    const Plan pl = make_plan(st, dtype, nq, k, n, d, (d * es + 15u) & ~15u, 148);
+    return pl.smem <= 227 * 1024 && pl.trigger >= k && pl.trigger + (uint32_t)(BN / pl.EG) <= pl.cap;
 }
 
 // defined in tc_path.cu

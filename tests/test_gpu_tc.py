@@ -59,7 +59,7 @@ def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
     engine.set_path(2)
     try:
         metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
-        for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33), (130, 128)):
+        for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33), (130, 128), (130, 129), (140, 257), (64, 300), (260, 512)):
             q = mv.synth_fill_host(dtype, 42, 0, nq, d)
             q[0] = db[n // 2]
             # one query tile of a Float32 space with k > 56 has no split-tf32 launch shape (96 KiB stages beside a
@@ -78,7 +78,10 @@ def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
 
 @pytest.mark.parametrize("dtype,n,d,nq,k", [(oracle.U8, 50000, 256, 96, 10), (oracle.U8, 3_000_000, 128, 200, 10),
                                             (oracle.I8, 2_000_000, 96, 130, 33), (oracle.F16, 1_000_000, 128, 130, 10),
-                                            (oracle.F32, 1_000_000, 128, 130, 10), (oracle.F32, 400_000, 768, 300, 100)])
+                                            (oracle.F32, 1_000_000, 128, 130, 10), (oracle.F32, 400_000, 768, 300, 100),
+                                            # k beyond 128: 512- and 1024-entry candidate buffers
+                                            (oracle.U8, 2_000_000, 128, 200, 300), (oracle.F16, 1_000_000, 128, 300, 512),
+                                            (oracle.F16, 600_000, 768, 260, 200), (oracle.F32, 300_000, 256, 260, 400)])
 def test_tensor_and_scan_paths_agree(engine, dtype, n, d, nq, k):
     # sizes beyond the CPU oracle: the two GPU paths (each checked against the oracle at small sizes) must agree
     # on every metric.  Many database tiles per CTA exercise the threshold / early-out logic of the K2 epilogue.
