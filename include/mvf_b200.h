@@ -202,7 +202,10 @@ MVF_API int mvf_shard_range(uint64_t n, int world, int rank, uint64_t* begin, ui
  * get_vector()+as_f32() of examples/similarity_search.rs:147-149. */
 MVF_API int mvf_gpu_space_upload(mvf_gpu* g, const mvf_space* s, mvf_gpu_space** out);
 /* same from caller memory: `rows` holds local_n rows of the shard starting at global row
- * row_base of a space with global_n rows */
+ * row_base of a space with global_n rows.  Shards must be contiguous and in rank order (rank r's rows precede rank
+ * r+1's): "lowest index on ties" is decided by (rank, local row).  Like every space creation on an engine with a
+ * communicator this is a collective call (the ranks exchange their first rows and the facts the kernel choice
+ * depends on). */
 MVF_API int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type, int metric,
                                     uint64_t local_n, uint32_t dimension, uint64_t row_base,
                                     uint64_t global_n, mvf_gpu_space** out);
@@ -264,8 +267,9 @@ MVF_API int mvf_gpu_space_get_vectors(mvf_gpu_space* s, const uint64_t* ids, uin
  * float spaces, squared distance for integer spaces, dot for InnerProduct, 1-cos for Cosine);
  * out_iscores (may be NULL) = exact int32 score for integer spaces with L2/InnerProduct.
  * With a communicator every rank must call it with the same queries; every rank gets the result.
- * Limits of this build (each answered with MVF_ERR_BUILD, never with a wrong result): a resident space holds
- * fewer than 2^32 rows; a row is at most 1 MiB; integer spaces have dimension <= 33025 (int32 accumulation,
+ * Limits of this build (each answered with MVF_ERR_BUILD, never with a wrong result): a resident SHARD holds
+ * fewer than 2^32 rows (candidates carry 32-bit local row ids; the space itself, row_base and the ids returned are
+ * 64-bit, so 8 GPUs take 8 x 2^32 rows); a row is at most 1 MiB; integer spaces have dimension <= 33025 (int32 accumulation,
  * SURVEY.md 8a); the per-CTA candidate lists of the scan kernel live in shared memory, so k is bounded by
  * 8 * pow2(8k) + dimension * 4 (or * 1 for integer spaces) <= ~227 KB, i.e. k <= 2048 for rows up to 24 KB;
  * the tensor-core path is taken for k <= 512 only (larger k run on the scan kernel).

@@ -166,6 +166,9 @@ struct mvf_gpu_space {
     unsigned char* rows_split = nullptr;  // Float32 spaces: the two tf32-exact planes [hi | lo] the batched path multiplies (K2')
     // Facts every rank of a sharded space agrees on (exchanged at upload): ranks that chose different kernels would
     // exchange candidate keys in different encodings.
+    uint64_t* rank_base = nullptr;        // [world] first global row of every rank's shard (device; cross-rank merges add it to the
+                                          // 32-bit LOCAL row ids the candidates carry, so only a shard is limited to 2^32 rows)
+    uint64_t min_shard_rows = 0;          // smallest non-empty shard over all ranks (spaces not cut by mvf_shard_range)
     bool ranged = false;                  // shard = mvf_shard_range(global_n, world, rank): the path is chosen from global_n
     uint64_t nonfinite_rows = 0;          // float spaces: rows with Inf/NaN components, over ALL shards
     bool split_everywhere = false;        // Float32 spaces: every rank holds its tf32 planes
@@ -299,6 +302,7 @@ bool launch_scan(mvf_gpu* g, const mvf_gpu_space* s, k::ScanParams p, int NQ, ui
                 fuse->in = p.cand; fuse->q_stride = (size_t)grid * p.k; fuse->list_stride = p.k; fuse->nlists = grid;
                 tail.counter = (uint32_t*)g->scan_counter.p;
                 tail.mp = *fuse;
+                if (!xchg) tail.mp.list_base = nullptr;          // a local merge: ids count from id_base
                 if (xchg) {
                     tail.exchange = 1; tail.x = *xchg;
                     tail.mp.out_packed = nullptr; tail.mp.out_ids = fin->ids; tail.mp.out_scores = fin->scores; tail.mp.out_iscores = fin->iscores;
@@ -329,7 +333,13 @@ void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
     // they do not fit, a segmented pass first reduces them to a few intermediate lists
     const size_t budget = std::min<size_t>(g->smem_optin, 200 * 1024);
     const size_t words = budget / 8;
-    if (mp.nlists > 0 && (size_t)mp.k * (32 + 2) <= words) {
+    // (a cross-rank merge -- list_base set -- is never segmented: its words name (rank, position), which an intermediate
+    // list would lose; with more ranks than fit one pass it takes the generic flavour below)
+    const bool ranked = mp.list_base != nullptr;
+    const bool one_pass = mp.nlists > 0 && (size_t)mp.k * (32 + 2) <= words &&
+                          mp.nlists <= (uint32_t)std::min<size_t>((words - (size_t)(mp.nlists <= 32 ? 8u : 32u) * mp.k) / mp.k,
+                                                                  (size_t)(mp.nlists <= 32 ? 8u : 32u) * 32 * k::kMergeMaxHeads);
+    if (mp.nlists > 0 && (size_t)mp.k * (32 + 2) <= words && (!ranked || one_pass)) {
         allow_smem(g, (const void*)k::merge_topk_tournament, budget);
         for (;;) {
             const uint32_t nwarps = mp.nlists <= 32 ? 8u : 32u;
@@ -346,7 +356,7 @@ void launch_merge(mvf_gpu* g, k::MergeParams mp, uint32_t nq) {
             const uint32_t seg_lists = (mp.nlists + segs - 1) / segs;
             g->merge_tmp[g->merge_tmp_flip].reserve((size_t)nq * segs * mp.k * 8);
             k::MergeParams sp = mp;
-            sp.seg_lists = seg_lists; sp.P = 0; sp.id_add = 0;
+            sp.seg_lists = seg_lists; sp.P = 0; sp.id_base = 0;
             sp.out_packed = (u64*)g->merge_tmp[g->merge_tmp_flip].p; sp.out_ids = nullptr; sp.out_scores = nullptr; sp.out_iscores = nullptr;
             const size_t smem = ((size_t)seg_lists + nwarps) * mp.k * 8;
             k::merge_topk_tournament<<<dim3(nq, segs), nwarps * 32, smem, g->stream>>>(sp);
@@ -397,7 +407,8 @@ uint64_t smallest_nonempty_shard(uint64_t global_n, int world) {
 }
 uint64_t decision_rows(const mvf_gpu_space* s) {
     const mvf_gpu* g = s->g;
-    if (!(s->ranged && g->world > 1)) return s->local_n;
+    if (g->world <= 1) return s->local_n;
+    if (!s->ranged) return s->min_shard_rows ? s->min_shard_rows : s->local_n;   // caller-cut shards: exchanged at creation
     return smallest_nonempty_shard(s->global_n, g->world);
 }
 bool host_queries_finite(const void* q, int qdtype, size_t count) {
@@ -514,7 +525,7 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         // merge the per-item lists; keys are K2 ranking values, decoded with the per-query constant
         k::MergeParams mp;
         mp.in = r.lists; mp.q_stride = (size_t)r.chunks * kk; mp.list_stride = kk; mp.nlists = r.chunks; mp.k = kk;
-        mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 1; mp.qconst = r.qconst;
+        mp.id_base = s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 1; mp.qconst = r.qconst;
         mp.out_packed = multi ? packed_local : nullptr;
         mp.out_ids = multi ? nullptr : d_ids; mp.out_scores = multi ? nullptr : d_scores; mp.out_iscores = multi ? nullptr : d_iscores;
         mp.ext_ids = s->ext_ids;
@@ -542,7 +553,8 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         k::MergeParams mp;
         mp.in = (const u64*)g->cand.p; mp.q_stride = 0; mp.list_stride = kk; mp.nlists = 0; mp.k = kk;
         mp.P = 0; mp.seg_lists = 0;
-        mp.id_add = (uint32_t)s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 0; mp.qconst = nullptr;
+        mp.id_base = s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 0; mp.qconst = nullptr;
+        mp.list_base = s->rank_base;                             // read only by a fused exchange (K1 + K3 + X1)
         const size_t o = (size_t)q0 * kk;
         mp.out_packed = multi ? packed_local + o : nullptr;
         mp.out_ids = multi ? nullptr : d_ids + o;
@@ -556,7 +568,7 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         if (s->local_n > 0) fused = launch_scan(g, s, p, NQ, &grid, &mp, fuse_x ? &ctx->x : nullptr, fuse_x ? &fin : nullptr);
         if (fused && fuse_x) { ctx->exchange_done = true; g->peer_searches++; }
         if (!fused) {
-            mp.q_stride = (size_t)grid * kk; mp.nlists = grid;
+            mp.q_stride = (size_t)grid * kk; mp.nlists = grid; mp.list_base = nullptr;
             launch_merge(g, mp, (uint32_t)NQ);
         }
         q0 += (uint32_t)NQ;
@@ -583,7 +595,7 @@ void search_final(mvf_gpu_space* s, const SearchCtx& ctx, uint64_t* d_ids, float
     const size_t cnt = (size_t)ctx.nq * ctx.kk;
     k::MergeParams mp;
     mp.in = (const u64*)g->gathered.p; mp.q_stride = ctx.kk; mp.list_stride = cnt; mp.nlists = (uint32_t)g->world; mp.k = ctx.kk;
-    mp.id_add = 0; mp.metric = ctx.metric; mp.dtype = s->dtype; mp.tc_mode = ctx.tc_keys ? 1 : 0; mp.qconst = ctx.tc_qconst;
+    mp.id_base = 0; mp.list_base = s->rank_base; mp.metric = ctx.metric; mp.dtype = s->dtype; mp.tc_mode = ctx.tc_keys ? 1 : 0; mp.qconst = ctx.tc_qconst;
     mp.out_packed = nullptr; mp.out_ids = d_ids; mp.out_scores = d_scores; mp.out_iscores = d_iscores;
     mp.ext_ids = s->ext_ids;
     launch_merge(g, mp, ctx.nq);
@@ -724,7 +736,7 @@ void search_exchange_peer(mvf_gpu_space* s, const SearchCtx& ctx, uint64_t* d_id
     x.mine = ctx.packed_local;
     k::MergeParams mp;
     mp.in = nullptr; mp.q_stride = 0; mp.list_stride = 0; mp.nlists = (uint32_t)g->world; mp.k = ctx.kk; mp.P = 0; mp.seg_lists = 0;
-    mp.id_add = 0; mp.metric = ctx.metric; mp.dtype = s->dtype; mp.tc_mode = ctx.tc_keys ? 1 : 0; mp.qconst = ctx.tc_qconst;
+    mp.id_base = 0; mp.list_base = s->rank_base; mp.metric = ctx.metric; mp.dtype = s->dtype; mp.tc_mode = ctx.tc_keys ? 1 : 0; mp.qconst = ctx.tc_qconst;
     mp.out_packed = nullptr; mp.out_ids = d_ids; mp.out_scores = d_scores; mp.out_iscores = d_iscores;
     mp.ext_ids = s->ext_ids;
     const size_t smem = ((size_t)g->world + 1) * ctx.kk * 8;
@@ -756,8 +768,8 @@ mvf_gpu_space* alloc_space(mvf_gpu* g, int dtype, int metric, uint64_t local_n, 
     if (metric == 255) throw MvfError::build_error("Custom distance metrics are not searchable");
     if (metric < 0 || metric > 2) throw MvfError::build_error("unsupported distance metric");
     if (d == 0) throw MvfError::build_error("vector space has dimension 0");
-    if (global_n > 0xffffffffull || local_n >= 0xffffffffull)
-        throw MvfError::build_error("spaces with more than 2^32 rows are not supported by this build");
+    if (local_n >= 0xffffffffull)             // candidates carry a 32-bit LOCAL row id; the space itself may be larger
+        throw MvfError::build_error("a resident shard holds fewer than 2^32 rows (shard the space over more GPUs)");
     const size_t es = element_size((DataType)dtype);
     if ((dtype == k::DT_I8 || dtype == k::DT_U8) && d > 33025)
         throw MvfError::build_error("integer spaces support dimension <= 33025 (int32 accumulation)");
@@ -824,6 +836,13 @@ void compute_norms(mvf_gpu_space* s) {
     }
 }
 
+// first global row of every rank's shard, kept on the device for the cross-rank merge
+void set_rank_bases(mvf_gpu_space* s, const std::vector<uint64_t>& bases) {
+    CUDA_CHECK(cudaSetDevice(s->g->device));
+    if (!s->rank_base) CUDA_CHECK(cudaMalloc((void**)&s->rank_base, bases.size() * 8));
+    CUDA_CHECK(cudaMemcpy(s->rank_base, bases.data(), bases.size() * 8, cudaMemcpyHostToDevice));
+}
+
 // Makes the path-deciding facts of a sharded space identical on every rank: the count of non-finite rows is summed
 // and "tf32 planes resident" is AND-ed over the ranks (one ncclAllGather of two words per rank; collective: every
 // rank creates the same spaces in the same order, as it must for searching them anyway).
@@ -831,17 +850,23 @@ void publish_facts(mvf_gpu_space* s) {
     mvf_gpu* g = s->g;
     if (!(g->world > 1 && g->comm)) return;
     if (g->parent_group) return;                          // members of a group engine: the group sums on the host
-    g->scalar_tmp.reserve(16 + 16 * (size_t)g->world);
-    uint64_t mine[2] = {s->nonfinite_rows, s->split_everywhere ? 1ull : 0ull};
+    g->scalar_tmp.reserve(32 + 32 * (size_t)g->world);
+    uint64_t mine[4] = {s->nonfinite_rows, s->split_everywhere ? 1ull : 0ull, s->row_base, s->local_n};
     unsigned char* base = (unsigned char*)g->scalar_tmp.p;
-    CUDA_CHECK(cudaMemcpyAsync(base, mine, 16, cudaMemcpyHostToDevice, g->stream));
-    nccl_check(nccl().AllGather(base, base + 16, 2, kNcclUint64, g->comm, g->stream), "ncclAllGather");
-    std::vector<uint64_t> all(2 * (size_t)g->world);
-    CUDA_CHECK(cudaMemcpyAsync(all.data(), base + 16, 16 * (size_t)g->world, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_CHECK(cudaMemcpyAsync(base, mine, 32, cudaMemcpyHostToDevice, g->stream));
+    nccl_check(nccl().AllGather(base, base + 32, 4, kNcclUint64, g->comm, g->stream), "ncclAllGather");
+    std::vector<uint64_t> all(4 * (size_t)g->world);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), base + 32, 32 * (size_t)g->world, cudaMemcpyDeviceToHost, g->stream));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
-    uint64_t nf = 0; bool split = true;
-    for (int r = 0; r < g->world; r++) { nf += all[2 * r]; split = split && all[2 * r + 1] != 0; }
-    s->nonfinite_rows = nf; s->split_everywhere = split;
+    uint64_t nf = 0, smallest = 0; bool split = true;
+    std::vector<uint64_t> bases((size_t)g->world);
+    for (int r = 0; r < g->world; r++) {
+        nf += all[4 * r]; split = split && all[4 * r + 1] != 0; bases[(size_t)r] = all[4 * r + 2];
+        const uint64_t rows = all[4 * r + 3];
+        if (rows && (!smallest || rows < smallest)) smallest = rows;
+    }
+    s->nonfinite_rows = nf; s->split_everywhere = split; s->min_shard_rows = smallest;
+    set_rank_bases(s, bases);
 }
 
 // Where the source rows live in a file, when they are a file mapping (lets the residency path re-map the range).
@@ -1054,7 +1079,7 @@ void free_space(mvf_gpu_space* s) {
     for (mvf_gpu_space* sh : s->shards) free_space(sh);
     if (!s->is_group()) {
         cudaSetDevice(s->g->device);
-        cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask); cudaFree(s->ext_ids); cudaFree(s->rows_split); cudaFree(s->acc_seed);
+        cudaFree(s->rows); cudaFree(s->norm); cudaFree(s->sq); cudaFree(s->mask); cudaFree(s->ext_ids); cudaFree(s->rows_split); cudaFree(s->acc_seed); cudaFree(s->rank_base);
     }
     delete s;
 }
@@ -1183,7 +1208,10 @@ mvf_gpu_space* wrap_group_space(mvf_gpu* grp, std::vector<mvf_gpu_space*>& shard
     S->row_base = s0->row_base; S->local_n = 0;
     uint64_t nf = 0; bool split = true, ranged = true;
     for (mvf_gpu_space* sh : shards) { S->local_n += sh->local_n; nf += sh->nonfinite_rows; split = split && sh->split_everywhere; ranged = ranged && sh->ranged; }
-    for (mvf_gpu_space* sh : shards) { sh->nonfinite_rows = nf; sh->split_everywhere = split; }
+    std::vector<uint64_t> bases;
+    uint64_t smallest = 0;
+    for (mvf_gpu_space* sh : shards) { bases.push_back(sh->row_base); if (sh->local_n && (!smallest || sh->local_n < smallest)) smallest = sh->local_n; }
+    for (mvf_gpu_space* sh : shards) { sh->nonfinite_rows = nf; sh->split_everywhere = split; sh->min_shard_rows = smallest; set_rank_bases(sh, bases); }
     S->nonfinite_rows = nf; S->split_everywhere = split; S->ranged = ranged;
     return S;
 }
@@ -1546,6 +1574,7 @@ int mvf_gpu_space_from_host(mvf_gpu* g, const void* rows, int data_type, int met
                 upload_rows(s, (const unsigned char*)rows + begin * rowbytes, count, rowbytes, false);
                 compute_norms(s);
                 CUDA_CHECK(cudaStreamSynchronize(e->stream));
+                publish_facts(s);                                // with a communicator: collective, like every space creation
             } catch (...) { free_space(s); throw; }
             return s;
         };

@@ -144,7 +144,10 @@ struct MergeParams {
     uint32_t nlists, k;
     uint32_t P;               // pow2 sort buffer (64-bit words), > k (bitonic flavour)
     uint32_t seg_lists;       // lists per CTA (tournament flavour)
-    uint32_t id_add;          // added to the low 32 bits of every valid candidate (shard row base)
+    uint64_t id_base;         // first GLOBAL row of the shard the candidates' 32-bit LOCAL row ids count from (used when ids are emitted)
+    const uint64_t* list_base = nullptr;   // cross-rank merge (list = rank): first global row of every rank's shard.  Candidates keep
+                              // LOCAL ids all the way, so only a shard (not the space) is limited to 2^32 rows; the merge orders
+                              // equal keys by (rank, position in the rank's sorted list) = by global row (shards are contiguous)
     u64* out_packed;          // [nq][k] or null
     uint64_t* out_ids;        // [nq][k] or null
     float* out_scores;        // [nq][k] or null
@@ -155,14 +158,18 @@ struct MergeParams {
     const uint64_t* ext_ids = nullptr;   // optional external id per GLOBAL row (vector_ids_block_index, schema/core.fbs:54): reported instead of the position
 };
 
-// decode one merged candidate into the caller's output arrays
-__device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, uint32_t j, u64 v) {
+// Cross-rank merges compare (key, rank, position j in the rank's list) instead of (key, local id): the low word of a
+// candidate is replaced on load and resolved back to a global row when the result is emitted.
+__device__ __forceinline__ u64 rank_word(u64 w, uint32_t list, uint32_t j) {
+    return w == kInf ? kInf : ((w & 0xffffffff00000000ull) | ((u64)list << 16) | j);
+}
+// decode one merged candidate into the caller's output arrays; gid = its global row
+__device__ __forceinline__ void emit_result_gid(const MergeParams& p, uint32_t q, uint32_t j, u64 v, uint64_t gid) {
     const bool valid = v != kInf;
-    if (valid) v += p.id_add;
     const size_t o = (size_t)q * p.k + j;
     if (p.out_packed) p.out_packed[o] = v;
     const uint32_t key = (uint32_t)(v >> 32);
-    if (p.out_ids) p.out_ids[o] = valid ? (p.ext_ids ? p.ext_ids[(uint32_t)v] : (uint64_t)(uint32_t)v) : ~0ull;
+    if (p.out_ids) p.out_ids[o] = valid ? (p.ext_ids ? p.ext_ids[gid] : gid) : ~0ull;
     const bool int_score = (p.dtype == DT_I8 || p.dtype == DT_U8) && p.metric != M_COS;
     if (int_score) {
         int s = (int)(key ^ 0x80000000u);
@@ -181,6 +188,18 @@ __device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, ui
         if (p.out_iscores) p.out_iscores[o] = 0;
         if (p.out_scores) p.out_scores[o] = valid ? s : __uint_as_float(0x7fc00000u);
     }
+}
+__device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, uint32_t j, u64 v) {
+    uint64_t gid = 0;
+    if (v != kInf) {
+        if (p.list_base != nullptr) {                          // ranked word: (list, position) -> the local id it stands for
+            const uint32_t r = (uint32_t)(v >> 16) & 0xffffu, jj = (uint32_t)v & 0xffffu;
+            gid = p.list_base[r] + (uint32_t)p.in[(size_t)q * p.q_stride + (size_t)r * p.list_stride + jj];
+        } else {
+            gid = p.id_base + (uint32_t)v;
+        }
+    }
+    emit_result_gid(p, q, j, v, gid);
 }
 
 // K3, fast flavour: the lists are individually sorted, so the k best of their union come out of a
@@ -269,8 +288,15 @@ __device__ __forceinline__ void exchange_gather(const ExchangeParams& x, uint32_
             __nanosleep(64);
             c = ld_cell(cell);
         }
-        cand[(size_t)r * k + j] = ((u64)c.z << 32) | c.x;
+        cand[(size_t)r * k + j] = rank_word(((u64)c.z << 32) | c.x, r, j);   // cross-rank order: (key, rank, position)
     }
+}
+// the global row a ranked word of query q stands for: local id from the cell it came from + that rank's first row
+__device__ __forceinline__ uint64_t exchange_gid(const ExchangeParams& x, const uint64_t* list_base, uint32_t q, uint32_t k, u64 w) {
+    if (w == kInf) return 0;
+    const uint32_t r = (uint32_t)(w >> 16) & 0xffffu, j = (uint32_t)w & 0xffffu;
+    const size_t slot0 = (size_t)x.buf * x.world * x.slot_cells;
+    return list_base[r] + ld_cell(x.window + slot0 + (size_t)r * x.slot_cells + (size_t)q * k + j).x;
 }
 // word j of query q of this rank into slot `rank` of every rank's window
 __device__ __forceinline__ void exchange_push(const ExchangeParams& x, uint32_t q, uint32_t k, uint32_t j, uint32_t r, u64 w) {
@@ -283,7 +309,7 @@ struct ScanTail {
     uint32_t* counter;        // CTAs finished so far (zero between launches); nullptr = no fused merge, K3 is launched separately
     MergeParams mp;           // in / q_stride / nlists describe ScanParams::cand of the same launch
     int exchange;             // K1 + K3 + X1 in one launch: the last CTA also pushes the merged list to every rank, waits for theirs
-    ExchangeParams x;         // and merges them (mp then describes the FINAL outputs; mp.id_add is applied before the push)
+    ExchangeParams x;         // and merges them (mp then describes the FINAL outputs, mp.list_base the ranks' first rows)
 };
 
 #ifdef MVF_ENGINE_TU   // non-template kernels: defined in engine.cu's translation unit only
@@ -300,7 +326,10 @@ __global__ void __launch_bounds__(1024) merge_topk(const MergeParams p) {
         for (uint32_t i = tid; i < room; i += blockDim.x) {
             size_t c = done + i;
             u64 v = kInf;
-            if (c < total) v = src[(c / p.k) * p.list_stride + (c % p.k)];
+            if (c < total) {
+                v = src[(c / p.k) * p.list_stride + (c % p.k)];
+                if (p.list_base != nullptr) v = rank_word(v, (uint32_t)(c / p.k), (uint32_t)(c % p.k));
+            }
             buf[p.k + i] = v;
         }
         done += room;
@@ -321,7 +350,11 @@ __global__ void __launch_bounds__(1024) merge_topk_tournament(const MergeParams 
     u64* lvl1 = cand + (size_t)p.seg_lists * p.k;           // [nwarps][k]
     const u64* src = p.in + (size_t)q * p.q_stride + (size_t)first * p.list_stride;
     const size_t total = (size_t)nlists * p.k;
-    for (size_t c = tid; c < total; c += blockDim.x) cand[c] = src[(c / p.k) * p.list_stride + (c % p.k)];
+    for (size_t c = tid; c < total; c += blockDim.x) {
+        u64 v = src[(c / p.k) * p.list_stride + (c % p.k)];
+        if (p.list_base != nullptr) v = rank_word(v, first + (uint32_t)(c / p.k), (uint32_t)(c % p.k));   // (never segmented: engine.cu)
+        cand[c] = v;
+    }
     __syncthreads();
     // level 1: warp w owns lists [w*per, min((w+1)*per, nlists))
     const uint32_t per = (nlists + nwarps - 1) / nwarps;
@@ -359,6 +392,7 @@ __global__ void __launch_bounds__(256) merge_topk_warp(const MergeParams p, uint
         const uint32_t li = (uint32_t)h * 32 + lane;
         head[h] = li < p.nlists ? __ldcg(src + (size_t)li * p.list_stride) : kInf;
         nxt[h] = (li < p.nlists && p.k > 1) ? __ldcg(src + (size_t)li * p.list_stride + 1) : kInf;
+        if (p.list_base != nullptr) { head[h] = rank_word(head[h], li, 0); nxt[h] = rank_word(nxt[h], li, 1); }
     }
     for (uint32_t j = 0; j < p.k; j++) {
         u64 mine = head[0];
@@ -381,6 +415,7 @@ __global__ void __launch_bounds__(256) merge_topk_warp(const MergeParams p, uint
                     idx[h]++;
                     head[h] = idx[h] < p.k ? nxt[h] : kInf;
                     nxt[h] = idx[h] + 1 < p.k ? __ldcg(src + (size_t)li * p.list_stride + idx[h] + 1) : kInf;
+                    if (p.list_base != nullptr) nxt[h] = rank_word(nxt[h], li, idx[h] + 1);
                 }
             }
         }
@@ -410,7 +445,7 @@ __global__ void __launch_bounds__(128) exchange_merge(const ExchangeParams x, co
     if (!x.do_merge || tid >= 32) return;
     u64* out = cand + (size_t)W * k;
     warp_tournament(cand, k, W, k, out, (int)tid);
-    for (uint32_t j = tid; j < k; j += 32) emit_result(p, q, j, out[j]);
+    for (uint32_t j = tid; j < k; j += 32) emit_result_gid(p, q, j, out[j], exchange_gid(x, p.list_base, q, k, out[j]));
 }
 #endif  // MVF_ENGINE_TU
 

@@ -176,8 +176,7 @@ __device__ __forceinline__ void fused_merge_tail(const ScanParams& p, const Scan
             } else {
                 // sharded search, small payload: this rank's list goes straight into every rank's window (X1)
                 for (uint32_t j = lane; j < k; j += 32) {
-                    u64 v = cand_s[j];
-                    if (v != kInf) v += tail.mp.id_add;
+                    const u64 v = cand_s[j];                    // local row ids travel; the merge adds every rank's base
                     for (uint32_t r = 0; r < tail.x.world; r++) exchange_push(tail.x, p.q0 + (uint32_t)q, k, j, r, v);
                 }
             }
@@ -191,9 +190,8 @@ __device__ __forceinline__ void fused_merge_tail(const ScanParams& p, const Scan
             if (warp == 0 && tail.x.do_merge) {
                 u64* out = xc + (size_t)tail.x.world * k;
                 warp_tournament(xc, k, tail.x.world, k, out, (int)lane);
-                MergeParams fin = tail.mp;
-                fin.id_add = 0;
-                for (uint32_t j = lane; j < k; j += 32) emit_result(fin, (uint32_t)q, j, out[j]);
+                for (uint32_t j = lane; j < k; j += 32)
+                    emit_result_gid(tail.mp, (uint32_t)q, j, out[j], exchange_gid(tail.x, tail.mp.list_base, p.q0 + (uint32_t)q, k, out[j]));
             }
             __syncthreads();
         }

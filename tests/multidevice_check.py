@@ -118,6 +118,24 @@ def main():
         gs.free()
         r.close()
 
+    # a space placed beyond 2^32 rows: local ids travel, member 0's merge adds every shard's first row in 64 bits
+    big = (1 << 34) + 99
+    for dtype, metric, n, d, k, nq in ((3, 0, 40000, 64, 10, 2), (1, 2, 50000, 64, 10, 70), (3, 0, 9000, 16, 100, 9)):
+        db = mv.synth_fill_host(dtype, 31, 0, n, d)
+        q = mv.synth_fill_host(dtype, 32, 0, nq, d)
+        if d == 16:
+            db[:] = db % 3                                         # exact ties across shard boundaries
+            q[:] = q % 3
+        queries = q if (dtype == 1 and nq >= 4) else np.stack([as_query(dtype, r) for r in q])
+        gs = eng.from_host(db, mv.DataType(dtype), mv.DistanceMetric(metric), row_base=big, global_n=big + n)
+        full = solo.from_host(db, mv.DataType(dtype), mv.DistanceMetric(metric), row_base=big, global_n=big + n)
+        got, want = gs.search(queries, k), full.search(queries, k)
+        if not (same(got, want) and got[0].min() >= big):
+            failures += 1
+            print("MISMATCH beyond 2^32 rows", (dtype, metric, n, d, k, nq))
+        gs.free()
+        full.free()
+
     # back-to-back searches with device-resident queries/results on device 0 (no host sync in between): the peer-memory
     # exchange alternates two buffers; 300 queued searches, each compared with the single-device engine afterwards
     n, d, k, rounds = 24000, 64, 10, 300

@@ -133,6 +133,29 @@ def main():
                 failures += 1
                 print("MISMATCH external ids / mask on shards, query", qi)
     gs.free()
+    # shards of a space of more than 2^32 rows (caller-cut shards, row_base far beyond 32 bits): local ids travel through the
+    # exchange, the cross-rank merge orders ties by (rank, position) and adds every rank's first row in 64 bits
+    big = (1 << 34) + 99
+    for dtype, metric, n, d, k, nq in ((3, 0, 40000, 64, 10, 2), (1, 2, 50000, 64, 10, 70), (3, 0, 9000, 16, 100, 9), (2, 1, 30000, 32, 10, 1)):
+        db = mv.synth_fill_host(dtype, 31, 0, n, d)
+        if dtype == 3 and d == 16:
+            db[:] = db % 3                                     # thousands of exact ties across the shard boundary
+        b, c = mv.shard_range(n, world, rank)
+        gs = eng.from_host(db[b:b + c], mv.DataType(dtype), mv.DistanceMetric(metric), row_base=big + b, global_n=big + n)
+        q = mv.synth_fill_host(dtype, 32, 0, nq, d)
+        if dtype == 3 and d == 16:
+            q[:] = q % 3
+        queries = q if (dtype == 1 and nq >= 4) else np.stack([as_query(dtype, r) for r in q])
+        ids, sc, isc = gs.search(queries, k)
+        if rank == 0:
+            full = solo.from_host(db, mv.DataType(dtype), mv.DistanceMetric(metric), row_base=big, global_n=big + n)
+            ids1, sc1, isc1 = full.search(queries, k)
+            if not (np.array_equal(ids, ids1) and np.array_equal(sc.view(np.uint32), sc1.view(np.uint32)) and np.array_equal(isc, isc1)
+                    and ids.min() >= big):
+                failures += 1
+                print("MISMATCH beyond 2^32 rows", (dtype, metric, n, d, k, nq))
+            full.free()
+        gs.free()
     # back-to-back searches without a host sync in between (device-resident queries and results): the peer-memory
     # exchange alternates two buffers and relies on nobody running two searches ahead of a reader -- 400 searches of
     # 1..3 queries queued at once, every result compared with the communicator-less engine afterwards

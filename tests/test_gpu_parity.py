@@ -121,6 +121,24 @@ def test_large_k_exercises_every_merge_flavour(engine, k):
         gs.free()
 
 
+def test_shard_of_a_space_beyond_2_32_rows(engine):
+    # candidates carry 32-bit LOCAL row ids; the shard's first global row is added in 64 bits when ids are emitted, so a
+    # resident shard may sit anywhere in a space of more than 2^32 rows (both kernels, every merge flavour's emit)
+    big = (1 << 33) + 12345
+    for dtype, n, d, nq, k in ((oracle.U8, 30_000, 64, 3, 10), (oracle.F16, 20_000, 96, 40, 10), (oracle.F32, 9_000, 32, 2, 300),
+                               (oracle.U8, 50_000, 128, 70, 33)):
+        db = mv.synth_fill_host(dtype, 71, 0, n, d)
+        gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2, row_base=big, global_n=big + n + 7)
+        assert (gs.row_base, gs.global_n) == (big, big + n + 7)
+        q = mv.synth_fill_host(dtype, 72, 0, nq, d)
+        queries = q if (dtype == oracle.F16 and nq >= 4) else np.stack([as_query(dtype, r) for r in q])
+        ids, sc, isc = gs.search(queries, k)
+        assert (ids >= big).all() and (ids < big + n).all()
+        check_batch(db, dtype, oracle.L2, queries.astype(np.float32) if dtype == oracle.F16 else queries, k,
+                    ids - np.uint64(big), sc, isc)
+        gs.free()
+
+
 def test_ties_resolve_to_lowest_index(engine):
     # 3 distinct byte values -> thousands of exact ties in every metric
     rng = np.random.default_rng(5)
