@@ -462,13 +462,16 @@ def main():
         batched["workload"] = describe(sib, n, d, dt, metric, bk, bbatch)
         batched["unit"] = "queries/s"
 
+    xinfo = eng.exchange_info()
     if rank == 0:
         line = {
             "metric": "brute-force top-k QPS", "value": main_leg["value"], "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_leg["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ARITH[dt], "data": "synthetic",
             "config": {"workload": describe(args.workload, n, d, dt, metric, k, batch), "rows_per_gpu": gs.local_n,
-                       "parallelism": "row-sharded x%d, one ncclAllGather of batch*k candidates" % world if world > 1 else "1 GPU",
+                       "parallelism": ("row-sharded x%d, one exchange of batch*k candidates per rank (%s)" % (
+                           world, "peer-memory kernel for <= 512 candidates, ncclAllGather above" if xinfo["peer_ready"]
+                           else "ncclAllGather; peer path off: %s" % xinfo["note"])) if world > 1 else "1 GPU",
                        "l2_policy": "database per GPU (%.2f GB) %s L2 (126 MB)" %
                                     (gs.local_n * d * es / 1e9, "exceeds" if gs.local_n * d * es > 126e6 else "FITS IN"),
                        "path": main_leg["path"]},
@@ -483,6 +486,7 @@ def main():
             line["batched"] = batched
         if world > 1:
             line["multirank_parity"] = multirank_parity
+            line["exchange"] = {"peer_searches": xinfo["peer_searches"], "nccl_searches": xinfo["nccl_searches"]}
         if not args.no_cpu:
             try:
                 line["cpu_baseline"] = cpu_baseline_leg(n, d, dt, metric, k)

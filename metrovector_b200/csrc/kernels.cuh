@@ -208,10 +208,13 @@ __device__ __forceinline__ void emit_result(const MergeParams& p, uint32_t q, ui
 // merges the 32 partial results.  ~100 cycles per output instead of a 16K-element sort.
 constexpr int kMergeMaxHeads = 4;   // list heads per lane -> up to 32*32*4 lists
 
+// minimum of one 64-bit word per lane: two hardware warp reductions (REDUX) on the halves instead of a five-round
+// 64-bit shuffle butterfly -- every output of every tournament below costs one of these
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { u64 o = shfl_xor_u64(v, off); v = o < v ? o : v; }
-    return v;
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ((u64)mh << 32) | ml;
 }
 
 // one warp merges `nl` sorted lists (list i at base + i*stride, k words each) into out[0..k)

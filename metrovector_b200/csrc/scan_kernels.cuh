@@ -239,6 +239,9 @@ template <int R, int LPR> struct RowsLeft { static constexpr int CNT = (R / LPR)
 // instead of a five-round shuffle butterfly: inserts are what a short scan is made of (config A: ~24 per warp for 42 rows).
 __device__ __forceinline__ void reg_list_insert(u64& mine, int k, u64 cand, u64& thr, int& pos, int lane) {
     if (lane == pos) mine = cand;
+    // while the list is filling up (thr is still a kInf filler) the fillers sit in lanes pos+1 .. k-1 -- they are consumed
+    // lowest lane first -- so the next maximum is known without looking: the first k inserts of a warp cost nothing
+    if (thr == kInf && pos + 1 < k) { pos++; return; }
     const bool real = lane < k;
     const uint32_t hi = real ? (uint32_t)(mine >> 32) : 0u, lo = real ? (uint32_t)mine : 0u;
     const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
@@ -279,13 +282,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (uint32_t i = threadIdx.x; i < NQ * p.P; i += blockDim.x) lists[i] = kInf;
-    stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
-
-    u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
-    u64 regl[NQ];                            // register-resident list entry of this lane (k <= 32)
-    const bool regmode = p.k <= 32;
-#pragma unroll
-    for (int q = 0; q < NQ; q++) { thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; regl[q] = lane < (int)p.k ? kInf : 0ull; }
 
     const uint32_t n = (uint32_t)p.n;
     const uint32_t pitch = p.pitch;
@@ -311,6 +307,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_topk_wide(const ScanPara
         for (int r = 0; r < R; r++) x[r] = ldg_stream16(ptr + (size_t)r * pitch);
         if (p.metric == M_COS) xn = p.norm[g * R + myrow];
     }
+    // (the first row tile is on its way from HBM while the queries are staged: on short scans -- BASELINE configs[0] is
+    // 42 rows per warp -- the prologue is a visible part of the search)
+    stage_queries<DT, NQ>(p, q_s, dpad, qc_s, red_s);
+
+    u64 thr[NQ]; int pos[NQ]; QueryConst qc[NQ];
+    u64 regl[NQ];                            // register-resident list entry of this lane (k <= 32)
+    const bool regmode = p.k <= 32;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { thr[q] = kInf; pos[q] = 0; qc[q] = qc_s[q]; regl[q] = lane < (int)p.k ? kInf : 0ull; }
+
     // the row loop is compiled twice: ragged rows (chunk count not a multiple of 32) zero the lanes past
     // the row end when a tile is consumed; the common shapes skip that work entirely
     auto run = [&](auto ragged_tag) {
