@@ -1,10 +1,12 @@
 """The N>1 path's host logic on CPU: world_size-2 gloo run (no GPU).
 
-What is exercised: the product's shard partition (mvf_shard_range), the packed (key << 32 | id)
-candidate words and their order-preserving key map (mvf_ordered_key_f32), one all_gather of nq*k
-words per rank, and the merge rule "ascending packed word == (score, lowest global index)".  The
-per-shard top-k itself comes from the CPU oracle here (the CUDA kernels are covered by -m gpu
-tests); the claim under test is that the sharded pipeline returns exactly the unsharded result.
+What is exercised: the product's shard partition (mvf_shard_range), the packed (key << 32 | LOCAL row
+id) candidate words and their order-preserving key map (mvf_ordered_key_f32), one all_gather of nq*k
+words per rank, and the cross-rank merge rule of kernels.cuh (rank_word / emit_result): equal keys
+order by (rank, position in the rank's sorted list) and the global row is list_base[rank] + local id
+in 64 bits -- so the space may sit beyond row 2^32.  The per-shard top-k itself comes from the CPU
+oracle here (the CUDA kernels are covered by -m gpu tests); the claim under test is that the sharded
+pipeline returns exactly the unsharded result.
 """
 import os
 import socket
@@ -31,7 +33,10 @@ def _pack(keys_u32, ids_u64):
     return ((keys_u32.astype(np.uint64) << np.uint64(32)) | ids_u64.astype(np.uint64))
 
 
-def _worker(rank, world, port, dtype, metric, n, d, k, nq, out_dir):
+INVALID = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _worker(rank, world, port, dtype, metric, n, d, k, nq, out_dir, offset=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,7 +48,8 @@ def _worker(rank, world, port, dtype, metric, n, d, k, nq, out_dir):
         for qi in range(nq):
             q = queries[qi].astype(np.float32) if dtype in (oracle.F32, oracle.F16) else queries[qi]
             if count:
-                ids, sc, isc = oracle.topk(shard, dtype, metric, q, k, row_base=begin)
+                ids, sc, isc = oracle.topk(shard, dtype, metric, q, k, row_base=begin + offset)
+                ids = ids - np.uint64(begin + offset)               # what travels is the row's position inside the shard
                 if dtype in (oracle.I8, oracle.U8) and metric != oracle.COS:
                     v = isc.astype(np.int64) if metric == oracle.L2 else -isc.astype(np.int64)
                     keys = (v + 2 ** 31).astype(np.uint32)
@@ -55,36 +61,51 @@ def _worker(rank, world, port, dtype, metric, n, d, k, nq, out_dir):
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)                                 # the one exchange step
         allc = np.stack([g.numpy().view(np.uint64) for g in gathered])   # [world, nq, k]
-        merged = np.sort(allc.transpose(1, 0, 2).reshape(nq, world * k), axis=1)[:, :k]
-        np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged)
+        bases = [mv.shard_range(n, world, r)[0] + offset for r in range(world)]
+        # ranked words: the low half names (rank, position) instead of the local id, which it is resolved back to
+        pos = (np.arange(world, dtype=np.uint64)[:, None, None] << np.uint64(16)) | np.arange(k, dtype=np.uint64)[None, None, :]
+        ranked = np.where(allc == INVALID, INVALID, (allc & np.uint64(0xFFFFFFFF00000000)) | pos)
+        top = np.sort(ranked.transpose(1, 0, 2).reshape(nq, world * k), axis=1)[:, :k]
+        keys = np.full((nq, k), np.uint32(0xFFFFFFFF), dtype=np.uint32)
+        gids = np.full((nq, k), INVALID, dtype=np.uint64)
+        for qi in range(nq):
+            for j in range(k):
+                w = int(top[qi, j])
+                if w == int(INVALID):
+                    continue
+                r, p = (w >> 16) & 0xFFFF, w & 0xFFFF
+                keys[qi, j] = w >> 32
+                gids[qi, j] = np.uint64(bases[r] + (int(allc[r, qi, p]) & 0xFFFFFFFF))
+        np.save(os.path.join(out_dir, "keys_%d.npy" % rank), keys)
+        np.save(os.path.join(out_dir, "gids_%d.npy" % rank), gids)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype,metric,n,d,k", [
-    (oracle.F32, oracle.L2, 1001, 24, 10),
-    (oracle.U8, oracle.L2, 777, 16, 25),      # tie-rich integers: lowest global index must win across shards
-    (oracle.F16, oracle.COS, 640, 32, 10),
-    (oracle.I8, oracle.IP, 3, 8, 5),          # fewer rows than k, one rank nearly empty
+@pytest.mark.parametrize("dtype,metric,n,d,k,offset", [
+    (oracle.F32, oracle.L2, 1001, 24, 10, 0),
+    (oracle.U8, oracle.L2, 777, 16, 25, 0),          # tie-rich integers: lowest global index must win across shards
+    (oracle.F16, oracle.COS, 640, 32, 10, 0),
+    (oracle.I8, oracle.IP, 3, 8, 5, 0),              # fewer rows than k, one rank nearly empty
+    (oracle.U8, oracle.L2, 777, 16, 25, (1 << 33) + 5),   # the same ties in a space placed beyond row 2^32
 ])
-def test_two_rank_sharded_search_equals_unsharded(tmp_path, dtype, metric, n, d, k):
+def test_two_rank_sharded_search_equals_unsharded(tmp_path, dtype, metric, n, d, k, offset):
     world, nq = 2, 3
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, dtype, metric, n, d, k, nq, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, dtype, metric, n, d, k, nq, str(tmp_path), offset), nprocs=world, join=True)
     db = oracle.synth(dtype, 42, 0, n, d)
     queries = oracle.synth(dtype, 43, 0, nq, d)
-    m0 = np.load(tmp_path / "merged_0.npy")
-    m1 = np.load(tmp_path / "merged_1.npy")
-    assert np.array_equal(m0, m1)                                    # every rank holds the same answer
+    k0, k1 = np.load(tmp_path / "keys_0.npy"), np.load(tmp_path / "keys_1.npy")
+    g0, g1 = np.load(tmp_path / "gids_0.npy"), np.load(tmp_path / "gids_1.npy")
+    assert np.array_equal(k0, k1) and np.array_equal(g0, g1)         # every rank holds the same answer
     for qi in range(nq):
         q = queries[qi].astype(np.float32) if dtype in (oracle.F32, oracle.F16) else queries[qi]
-        ids, sc, isc = oracle.topk(db, dtype, metric, q, k)
-        got = m0[qi]
-        valid = got != np.uint64(0xFFFFFFFFFFFFFFFF)
+        ids, sc, isc = oracle.topk(db, dtype, metric, q, k, row_base=offset)
+        valid = g0[qi] != INVALID
         assert int(valid.sum()) == len(ids)
-        assert (got[valid] & np.uint64(0xFFFFFFFF)).tolist() == ids.tolist()
+        assert g0[qi][valid].tolist() == ids.tolist()
         if dtype in (oracle.F32, oracle.F16) or metric == oracle.COS:
-            back = np.array([mv.ordered_key_to_f32(int(x >> np.uint64(32))) for x in got[valid]], dtype=np.float32)
+            back = np.array([mv.ordered_key_to_f32(int(x)) for x in k0[qi][valid]], dtype=np.float32)
             want = -sc if metric == oracle.IP else sc
             assert np.array_equal(back.view(np.uint32), (want + np.float32(0)).view(np.uint32))
 
