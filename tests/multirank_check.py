@@ -36,6 +36,8 @@ def main():
     failures = 0
     cases = [(0, 0, 20000, 128, 10, 3), (1, 2, 30001, 96, 10, 2), (3, 0, 50000, 128, 25, 4), (2, 1, 7, 16, 5, 2),
              (3, 2, 40000, 64, 10, 1), (0, 1, 1000, 768, 100, 9),
+             # large k inside the peer-exchange payload (<= 512 candidates): fused into the scan launch / its own kernel
+             (3, 0, 30000, 64, 500, 1), (0, 2, 20000, 32, 256, 2),
              # batches that take the tensor-core path on every rank (keys are K2 ranking values until the final merge)
              (3, 0, 60000, 128, 10, 40), (1, 2, 50000, 128, 10, 70), (1, 0, 50000, 64, 33, 130), (2, 1, 40000, 96, 10, 16),
              # Float32 batches: the split-tf32 form (K2')
