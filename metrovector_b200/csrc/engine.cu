@@ -1550,6 +1550,7 @@ int mvf_gpu_comm_init(mvf_gpu* g, const void* unique_id_128_bytes, int rank, int
     return guard([&] { EngineLock engine_lock(g->mu);
         require_single(g, "mvf_gpu_comm_init");
         if (world < 1 || rank < 0 || rank >= world) throw MvfError::nccl("invalid rank/world");
+        if (g->comm) throw MvfError::nccl("this engine already has a communicator");
         CUDA_CHECK(cudaSetDevice(g->device));
         g->rank = rank; g->world = world;
         if (world == 1) return;
