@@ -550,12 +550,14 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
         // merge the per-item lists; keys are K2 ranking values, decoded with the per-query constant
         k::MergeParams mp;
         mp.in = r.lists; mp.q_stride = (size_t)r.chunks * kk; mp.list_stride = kk; mp.nlists = r.chunks; mp.k = kk;
-        mp.id_base = s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = 1; mp.qconst = r.qconst;
+        // (integer cosine: the tensor kernel's candidates already carry the exact final keys, nothing to decode)
+        const bool final_keys = (s->dtype == k::DT_I8 || s->dtype == k::DT_U8) && metric == k::M_COS;
+        mp.id_base = s->row_base; mp.metric = metric; mp.dtype = s->dtype; mp.tc_mode = final_keys ? 0 : 1; mp.qconst = r.qconst;
         mp.out_packed = multi ? packed_local : nullptr;
         mp.out_ids = multi ? nullptr : d_ids; mp.out_scores = multi ? nullptr : d_scores; mp.out_iscores = multi ? nullptr : d_iscores;
         mp.ext_ids = s->ext_ids;
         launch_merge(g, mp, nq);
-        ctx->tc_keys = true; ctx->tc_qconst = r.qconst;
+        ctx->tc_keys = !final_keys; ctx->tc_qconst = r.qconst;
         return;
     }
     g->last_path = 1;

@@ -21,9 +21,13 @@ static const void* pick_form(int cl, bool pair) {
 
 #define TC_CAT2(a, b, c) a##b##_eg##c
 #define TC_CAT(a, b, c) TC_CAT2(a, b, c)
-// kernel_k<KIND>_eg<EG>(l2, cl, pair): MODE 0 ranks |x|^2 - 2 q.x (L2), MODE 1 ranks -q.x / |x| or -q.x
-const void* TC_CAT(kernel_k, TC_KIND, TC_EG)(bool l2, int cl, bool pair) {
-    return l2 ? pick_form<TC_KIND, 0, TC_EG>(cl, pair) : pick_form<TC_KIND, 1, TC_EG>(cl, pair);
+// kernel_k<KIND>_eg<EG>(mode, cl, pair): MODE 0 ranks |x|^2 - 2 q.x (L2), MODE 1 ranks -q.x / |x| or -q.x, MODE 3 is the
+// integer kinds' cosine (approximate common path, exact keys for the candidates)
+const void* TC_CAT(kernel_k, TC_KIND, TC_EG)(int mode, int cl, bool pair) {
+#if TC_KIND == 1
+    if (mode == 3) return pick_form<TC_KIND, 3, TC_EG>(cl, pair);
+#endif
+    return mode == 0 ? pick_form<TC_KIND, 0, TC_EG>(cl, pair) : pick_form<TC_KIND, 1, TC_EG>(cl, pair);
 }
 
 }  // namespace tc

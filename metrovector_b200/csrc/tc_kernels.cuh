@@ -39,6 +39,7 @@ struct TcParams {
     const float* norm;             // sqrt(sum x^2) per resident row
     const float* sq;               // sum x^2 per row (f32, or int32 bits for integer spaces)
     const uint32_t* mask;          // optional row mask (bit set = excluded), same layout as ScanParams::mask
+    const float* qconst;           // per query constant (prep_queries); the kernel itself reads it for integer cosine only (|q|)
     const int* acc_seed;           // integer L2: per row, padded to whole tiles, what the accumulator column starts from:
                                    // -(|x|^2 >> 1) for live rows, kSeedDead for rows past the end / deleted / filtered out
     u64* cand;                     // [gridDim.x][EG][BM][cap] scratch candidate buffers
@@ -307,6 +308,10 @@ __device__ __forceinline__ u64 compact_buffer(u64* gbuf, int cnt, int k, int cap
 // MODE selects the ranking value computed from the accumulator `a` and the per-column parameter:
 //   MODE 0  (L2)            s = prm - 2a        prm = |x|^2           (float: fma; int: exact)
 //   MODE 1  (cosine / dot)  s = a * prm         prm = -1/|x| or -1    (float)   |  s = -a (int dot)
+//   MODE 3  (integer cosine) the exact key is 1 - a / (|q| |x|) in the scan kernel's float operations (a division per
+//           element); the common path tests the approximate s = float(a) * (-1/|x|) against a bound widened by more than
+//           the rounding of both forms, and only the rare candidates get the exact key -- which is what their buffers,
+//           the shared bounds and the merges then compare, so the result is bit-identical to the scan kernel's.
 // CL = 2: CTA pairs (thread-block clusters) work on the same database tiles for two different query
 // tiles; each CTA fetches half of the 256-row database tile and TMA-multicasts it into both CTAs'
 // shared memory, so L2 -> SM operand traffic per tile drops from 576 KB to 384 KB and the pair
@@ -338,6 +343,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     // IADD3 (|x|^2 - 2a) and the parameter LDS of the old form were 2/3 of the epilogue's instructions on short
     // rows (config E batched: 512 MMA cycles per tile against ~2300 measured).
     constexpr bool INIT_ACC = INT && MODE == 0;
+    constexpr bool ICOS = INT && MODE == 3;
+    static_assert(MODE != 3 || INT, "MODE 3 is the integer cosine form");
     constexpr int EPI_GROUPS = EG, EPI_THREADS = 128 * EG, EPI_COLS = BN / EG, LDG = 1;
     constexpr int PSLOTS = 3;                                           // column-parameter slots per epilogue warp (tc_path.hpp smem_bytes)
     constexpr int SB = stage_bytes_of(KIND, PAIR);
@@ -549,7 +556,7 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             float v = 0.f;
             if (in) {
                 if (MODE == 0) v = p.sq[row];                             // |x|^2 (int32 bits for integer spaces)
-                else if (!INT && p.metric == k::M_COS) v = p.norm[row];
+                else if ((!INT && p.metric == k::M_COS) || ICOS) v = p.norm[row];
             }
             *raw = v;
         };
@@ -559,8 +566,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             *live = ok;
             if (!ok) return __int_as_float(0);
             if (MODE == 0) return raw;
-            if (INT) return __int_as_float(0);
-            if (p.metric == k::M_COS) return raw > 0.f ? -1.0f / raw : 0.0f;
+            if (INT && !ICOS) return __int_as_float(0);
+            if (ICOS || p.metric == k::M_COS) return raw > 0.f ? -1.0f / raw : 0.0f;
             return -1.0f;
         };
         // publishes the parameters of database tile t in slot `slot` of the warp's private slice (from raw words loaded earlier)
@@ -666,13 +673,27 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             //     runs on the rare candidates only (no overflow: |t >> 1| <= 2^30).
             int thr_i = 0x7fffffff;
             [[maybe_unused]] int thr_s = 0x7fffffff;
+            // integer cosine: |q| (as the scan kernel computes it), the widened bound on the approximate ranking value and
+            // the exact bound on the key
+            [[maybe_unused]] const float qn = (ICOS && q < p.nq) ? p.qconst[q] : 0.0f;
+            [[maybe_unused]] float thr_fc = __int_as_float(0x7f800000);
+            [[maybe_unused]] uint32_t thr_ck = 0xffffffffu;
             auto set_thr_i = [&](int t) { if (INIT_ACC) { thr_s = t; thr_i = -(t >> 1) - 1; } else thr_i = ~t; };
             auto refresh_threshold = [&]() {
-                if (q >= p.nq) { thr_f = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }   // padding row of the query tile: nothing passes
-                if (thr_key == 0xffffffffu) { thr_f = __int_as_float(0x7f800000); set_thr_i(0x7fffffff); return; }
+                if (q >= p.nq) { thr_f = thr_fc = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }   // padding row of the query tile: nothing passes
+                if (thr_key == 0xffffffffu) { thr_f = thr_fc = __int_as_float(0x7f800000); thr_ck = 0xffffffffu; set_thr_i(0x7fffffff); return; }
                 const bool ties = thr_key < loc_key;
-                if (!ties && thr_key == 0) { thr_f = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }
+                if (!ties && thr_key == 0) { thr_f = thr_fc = __int_as_float(0xff800000); set_thr_i((int)0x80000000); return; }
                 const uint32_t ck = ties ? thr_key : thr_key - 1;
+                if (ICOS) {
+                    // key <= ck  <=>  1 - a / (|q||x|) <= tv; in the approximate form s = -a / |x|:  s <= (tv - 1) |q|.  The bound
+                    // is widened by the rounding of both forms (1 - x rounds to 6e-8 absolute, the products to ~1e-7 relative);
+                    // a zero query (every key is exactly 1) sends everything to the exact test.
+                    thr_ck = ck;
+                    const float tv = k::unordered_f32(ck);
+                    thr_fc = (qn > 0.0f && tv == tv) ? (tv - 1.0f + 4e-7f + 4e-6f * fabsf(tv - 1.0f)) * qn : __int_as_float(0x7f800000);
+                    return;
+                }
                 if (INT) set_thr_i((int)(ck ^ 0x80000000u)); else thr_f = k::unordered_f32(ck);
             };
             refresh_threshold();
@@ -693,7 +714,13 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 for (int j = 0; j < 32; j++) {
                     if (mask & (1u << j)) {
                         uint32_t key;
-                        if (INT) {
+                        if (ICOS) {
+                            // the scan kernel's key, operation for operation (scan_kernels.cuh finalize): 1 - a / (|q| |x|), zero norm -> 1
+                            const float den = __fmul_rn(qn, p.norm[id0 + j]);
+                            const float vv = den > 0.0f ? __fsub_rn(1.0f, __fdiv_rn((float)(int)v[j], den)) : 1.0f;
+                            key = k::ordered_f32(vv);
+                            if (key > thr_ck) continue;                // passed the widened bound only
+                        } else if (INT) {
                             // exact integer ranking value: s = (|x|^2 & 1) - 2r (L2; the parity comes from the row's |x|^2) or -a (dot)
                             const int s = INIT_ACC ? (__float_as_int(p.sq[id0 + j]) & 1) - 2 * (int)v[j] : -(int)v[j];
                             if (INIT_ACC && s > thr_s) continue;       // passed the conservative bound on r only
@@ -745,13 +772,30 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         }
                         TC_STAT_BEGIN(c_p);
                         const uint32_t id0 = t * BN + grp * EPI_COLS + cc * 32;
-                        int m0 = (int)0x80000000, m1 = (int)0x80000000;       // two chains: max of a (dot) / of r (L2)
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) { m0 = max(m0, (int)v[j]); m1 = max(m1, (int)v[j + 1]); }
                         uint32_t mask = 0;
-                        if (max(m0, m1) > thr_i) {
+                        if constexpr (ICOS) {
+                            // approximate ranking value s = float(a) * (-1 / |x|) and its minimum over the group
+                            const float4* pr4 = reinterpret_cast<const float4*>(my_prm + slot * EPI_COLS + cc * 32);
+                            float f0 = __int_as_float(0x7f800000), f1 = f0;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) if ((int)v[j] > thr_i) mask |= 1u << j;
+                            for (int j4 = 0; j4 < 8; j4++) {
+                                const float4 pq = pr4[j4];
+                                f0 = fminf(f0, fminf((float)(int)v[4 * j4] * pq.x, (float)(int)v[4 * j4 + 2] * pq.z));
+                                f1 = fminf(f1, fminf((float)(int)v[4 * j4 + 1] * pq.y, (float)(int)v[4 * j4 + 3] * pq.w));
+                            }
+                            if (fminf(f0, f1) <= thr_fc) {
+                                const float* prs = my_prm + slot * EPI_COLS + cc * 32;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) if ((float)(int)v[j] * prs[j] <= thr_fc) mask |= 1u << j;
+                            }
+                        } else {
+                            int m0 = (int)0x80000000, m1 = (int)0x80000000;   // two chains: max of a (dot) / of r (L2)
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) { m0 = max(m0, (int)v[j]); m1 = max(m1, (int)v[j + 1]); }
+                            if (max(m0, m1) > thr_i) {
+#pragma unroll
+                                for (int j = 0; j < 32; j++) if ((int)v[j] > thr_i) mask |= 1u << j;
+                            }
                         }
                         if (!INIT_ACC) mask &= vs[cc];                   // rows past the end, deleted or filtered out (INIT_ACC: dead seeds)
                         if (dump) {
@@ -759,7 +803,8 @@ gemm_topk_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             for (int j = 0; j < 32; j++) {
                                 const bool in = id0 + j < n32;
                                 p.dump[((size_t)mt * BM + qrow) * ((size_t)p.ntiles * BN) + id0 + j] =
-                                    (float)(INIT_ACC ? (in ? (__float_as_int(p.sq[id0 + j]) & 1) - 2 * (int)v[j] : 0) : -(int)v[j]);
+                                    ICOS ? (float)(int)v[j] * my_prm[slot * EPI_COLS + cc * 32 + j]
+                                         : (float)(INIT_ACC ? (in ? (__float_as_int(p.sq[id0 + j]) & 1) - 2 * (int)v[j] : 0) : -(int)v[j]);
                             }
                         }
                         if (mask) append_hits(mask, v, id0);
@@ -923,7 +968,7 @@ __global__ void __launch_bounds__(128) prep_queries(const void* q, unsigned char
     if (threadIdx.x == 0) {
         float f = rf[0] + rf[1] + rf[2] + rf[3]; int i = ri[0] + ri[1] + ri[2] + ri[3];
         float c;
-        if (INT) c = metric == k::M_L2 ? __int_as_float(i) : 0.f;
+        if (INT) c = metric == k::M_L2 ? __int_as_float(i) : (metric == k::M_COS ? __fsqrt_rn((float)i) : 0.f);   // cosine: |q| as the scan kernel computes it
         else if (metric == k::M_COS) { float nm = sqrtf(f); c = nm > 0.f ? 1.0f / nm : 0.0f; }
         else c = f;
         qconst[qi] = c;

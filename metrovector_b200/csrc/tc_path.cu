@@ -95,7 +95,7 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
     } else { map_q2 = map_q; map_x2 = map_x; }
 
     TcParams p;
-    p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.acc_seed = a.acc_seed; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
+    p.norm = a.norm; p.sq = a.sq; p.mask = a.mask; p.acc_seed = a.acc_seed; p.qconst = (const float*)st.qconst.p; p.cand = (u64*)st.cand.p; p.out_lists = (u64*)st.lists.p; p.dump = nullptr;
     p.gthr = (uint32_t*)st.gthr.p;
     p.gslot = p.gthr + bound_rows;
     p.n = a.n; p.nq = a.nq; p.k = a.k; p.cap = cap;
@@ -122,8 +122,8 @@ SearchResult run(TcState& st, const SearchArgs& a, cudaStream_t stream, int sm_c
         st.dump.reserve((size_t)mtiles * BM * (size_t)ntiles * BN * 4);
         p.dump = (float*)st.dump.p;
     }
-    const bool l2 = a.metric == k::M_L2;
-    const void* fn = select_kernel(kind, EG, l2, (int)CL, pair);
+    const int mode = a.metric == k::M_L2 ? 0 : ((kind == KIND_I8 && a.metric == k::M_COS) ? 3 : 1);
+    const void* fn = select_kernel(kind, EG, mode, (int)CL, pair);
     const size_t smem = pl.smem;
     // per device and cheap; set on every launch so a second engine on another GPU of this process gets it too
     TC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

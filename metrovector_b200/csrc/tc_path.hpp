@@ -140,8 +140,8 @@ inline uint32_t cap_for_k(uint32_t k, int eg) {
     return cap;
 }
 
-// K2 takes f16 spaces with f16 queries, f32 spaces with f32 queries (split tf32) and int8/uint8 spaces (any metric
-// except integer cosine, whose exact definition needs a division per element), k <= MAX_K (512).  `n` must be a value every
+// K2 takes f16 spaces with f16 queries, f32 spaces with f32 queries (split tf32) and int8/uint8 spaces (every metric:
+// integer cosine, whose exact definition needs a division per element, forms it for the candidates only), k <= MAX_K (512).  `n` must be a value every
 // rank of a sharded space agrees on (engine.cu passes the smallest non-empty shard): ranks on different paths would
 // exchange keys in different encodings.
 struct TcState;
@@ -152,7 +152,8 @@ inline bool eligible(const TcState& st, int path, int dtype, int qdtype, int met
     if (path == 1) return false;
     const bool f16 = dtype == 1 && qdtype == 1;
     const bool f32 = dtype == 0 && qdtype == 0;
-    const bool i8 = (dtype == 2 || dtype == 3) && qdtype == dtype && metric != 2;
+    const bool i8 = (dtype == 2 || dtype == 3) && qdtype == dtype;
+    (void)metric;
     if (!(f16 || f32 || i8)) return false;
     if (k > (uint32_t)MAX_K || n == 0 || d == 0) return false;
     // split tf32: the tensor core's f32 accumulation over 3 * d / 8 MMA steps leaves ~4e-6 |q||x| at d = 768 (measured,
@@ -230,15 +231,16 @@ void split_rows_tf32(const unsigned char* rows, uint64_t n, uint32_t pitch, unsi
 void release(TcState& st);
 
 // defined in tc_inst.cu (compiled once per kind x epilogue-group count): kernel_k<KIND>_eg<EG>
-const void* kernel_k0_eg2(bool l2, int cl, bool pair);
-const void* kernel_k0_eg4(bool l2, int cl, bool pair);
-const void* kernel_k1_eg2(bool l2, int cl, bool pair);
-const void* kernel_k1_eg4(bool l2, int cl, bool pair);
-const void* kernel_k2_eg2(bool l2, int cl, bool pair);
-inline const void* select_kernel(int kind, int eg, bool l2, int cl, bool pair) {
-    if (kind == KIND_TF32) return kernel_k2_eg2(l2, cl, pair);
-    if (kind == KIND_I8) return eg == 4 ? kernel_k1_eg4(l2, cl, pair) : kernel_k1_eg2(l2, cl, pair);
-    return eg == 4 ? kernel_k0_eg4(l2, cl, pair) : kernel_k0_eg2(l2, cl, pair);
+const void* kernel_k0_eg2(int mode, int cl, bool pair);
+const void* kernel_k0_eg4(int mode, int cl, bool pair);
+const void* kernel_k1_eg2(int mode, int cl, bool pair);
+const void* kernel_k1_eg4(int mode, int cl, bool pair);
+const void* kernel_k2_eg2(int mode, int cl, bool pair);
+// mode: 0 L2, 1 dot / float cosine, 3 integer cosine (tc_kernels.cuh)
+inline const void* select_kernel(int kind, int eg, int mode, int cl, bool pair) {
+    if (kind == KIND_TF32) return kernel_k2_eg2(mode, cl, pair);
+    if (kind == KIND_I8) return eg == 4 ? kernel_k1_eg4(mode, cl, pair) : kernel_k1_eg2(mode, cl, pair);
+    return eg == 4 ? kernel_k0_eg4(mode, cl, pair) : kernel_k0_eg2(mode, cl, pair);
 }
 
 }  // namespace tc

@@ -42,6 +42,8 @@ def main():
              # batches that take the tensor-core path on every shard
              (3, 0, 60000, 128, 10, 40), (1, 2, 50000, 128, 10, 70), (1, 0, 50000, 64, 33, 130), (2, 1, 40000, 96, 10, 16),
              (0, 0, 60000, 96, 10, 48), (0, 2, 50000, 128, 10, 200),
+             # integer cosine on the tensor path: its candidates carry final keys (nothing to decode after the exchange)
+             (3, 2, 50000, 128, 10, 40), (2, 2, 40000, 64, 33, 130),
              # the tail shard falls under the tensor path's minimum while the others do not: one choice for all shards
              (1, 2, ndev * 4096 - 1, 64, 10, 8), (3, 0, ndev * 4096 - 1, 128, 10, 16)]
     for dtype, metric, n, d, k, nq in cases:

@@ -42,6 +42,8 @@ def main():
              (3, 0, 60000, 128, 10, 40), (1, 2, 50000, 128, 10, 70), (1, 0, 50000, 64, 33, 130), (2, 1, 40000, 96, 10, 16),
              # Float32 batches: the split-tf32 form (K2')
              (0, 0, 60000, 96, 10, 48), (0, 2, 50000, 128, 10, 200),
+             # integer cosine on the tensor path: its candidates carry final keys (nothing to decode after the exchange)
+             (3, 2, 50000, 128, 10, 40), (2, 2, 40000, 64, 33, 130),
              # the tail shard falls under the tensor path's minimum (4096 rows) while the others do not: every rank must
              # make the same choice or the exchanged keys are in two encodings
              (1, 2, world * 4096 - 1, 64, 10, 8), (3, 0, world * 4096 - 1, 128, 10, 16)]

@@ -31,11 +31,13 @@ def test_raw_contraction_matches_numpy(engine, dtype, d):
     db = mv.synth_fill_host(dtype, 31, 0, n, d)
     q = mv.synth_fill_host(dtype, 32, 0, nq, d)
     gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
-    metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
-    for metric in metrics:
+    for metric in (oracle.L2, oracle.IP, oracle.COS):
         got = gs.tc_dump(q, k=10, metric=metric)[:nq, :n]
         want = _rank_values(db, q, dtype, metric)
-        if dtype in FLOATS:
+        if dtype not in FLOATS and metric == oracle.COS:
+            # integer cosine: the common path's approximate ranking value float(a) * (-1 / |x|) (the candidates' keys are exact)
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-6 * np.abs(want).max()), np.abs(got - want).max()
+        elif dtype in FLOATS:
             scale = np.abs(want).max()
             # f16 products are exact in f32; the split-tf32 product drops a 2^-22 term: both far inside 1e-5 of the scale
             assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * scale), (metric, np.abs(got - want).max())
@@ -58,7 +60,7 @@ def test_tensor_path_search_matches_oracle(engine, dtype, d, n):
     gs = engine.from_host(db, DT[dtype], mv.DistanceMetric.L2)
     engine.set_path(2)
     try:
-        metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
+        metrics = (oracle.L2, oracle.IP, oracle.COS)      # integers too: their cosine keys are formed exactly for the candidates
         for nq, k in ((200, 10), (64, 100), (3, 1), (129, 33), (130, 128), (130, 129), (140, 257), (64, 300), (260, 512)):
             q = mv.synth_fill_host(dtype, 42, 0, nq, d)
             q[0] = db[n // 2]
@@ -88,8 +90,7 @@ def test_tensor_and_scan_paths_agree(engine, dtype, n, d, nq, k):
     gs = engine.synthetic(DT[dtype], mv.DistanceMetric.L2, n, d, 51)
     q = mv.synth_fill_host(dtype, 52, 0, nq, d)
     try:
-        # integer cosine stays on the scan path by design (exact definition needs a division per element)
-        for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)):
+        for metric in (oracle.L2, oracle.IP, oracle.COS):
             engine.set_path(1)
             a = gs.search(q, k, metric=metric)
             engine.set_path(2)
@@ -98,8 +99,9 @@ def test_tensor_and_scan_paths_agree(engine, dtype, n, d, nq, k):
             if dtype in FLOATS:                                              # accumulation order differs
                 assert np.allclose(a[1], b[1], rtol=1e-4, atol=1e-5), metric
                 assert ids_agree_within_tolerance(metric, a[0], a[1], b[0], b[1]), metric
-            else:                                                            # integers: bit-identical
+            else:                                                            # integers: bit-identical (cosine: the float score bits)
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]), metric
+                assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), metric
     finally:
         engine.set_path(0)
         gs.free()
@@ -128,6 +130,20 @@ def test_ties_and_degenerate_queries_on_the_tensor_path(engine):
         check_batch(dbu, oracle.U8, oracle.L2, qu[:4], 64, ids[:4], sc[:4], isc[:4])
         check_batch(dbu, oracle.U8, oracle.L2, qu[-2:], 64, ids[-2:], sc[-2:], isc[-2:])
         gu.free()
+        # integer cosine: few distinct bytes -> many exactly equal keys; zero rows (distance 1) and a zero query
+        dbc = rng.integers(0, 3, (50000, 64)).astype(np.uint8)
+        dbc[100:140] = 0
+        dbc[20000:20040] = dbc[:40]
+        gc = engine.from_host(dbc, mv.DataType.UInt8, mv.DistanceMetric.Cosine)
+        qc = rng.integers(0, 3, (140, 64)).astype(np.uint8)
+        qc[0] = 0
+        qc[1] = dbc[5]
+        ids, sc, isc = gc.search(qc, 40)
+        assert engine.profile_read()["last_path"] == 2
+        check_batch(dbc, oracle.U8, oracle.COS, qc[:6], 40, ids[:6], sc[:6], isc[:6])
+        check_batch(dbc, oracle.U8, oracle.COS, qc[-3:], 40, ids[-3:], sc[-3:], isc[-3:])
+        assert ids[0].tolist() == list(range(40)) and (sc[0] == 1.0).all()
+        gc.free()
     finally:
         engine.set_path(0)
 
@@ -146,7 +162,7 @@ def test_every_kernel_form_matches_oracle(env, monkeypatch):
             db = mv.synth_fill_host(dtype, 61, 0, n, d)
             gs = eng.from_host(db, DT[dtype], mv.DistanceMetric.L2)
             q = mv.synth_fill_host(dtype, 62, 0, 300, d)
-            for metric in ((oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)):
+            for metric in (oracle.L2, oracle.IP, oracle.COS):
                 ids, sc, isc = gs.search(q, 10, metric=metric)
                 assert eng.profile_read()["last_path"] == 2
                 qq = q.astype(np.float32) if dtype == oracle.F16 else q
@@ -181,8 +197,7 @@ def test_randomised_shapes_on_the_tensor_path(engine):
             q = mv.synth_fill_host(dtype, 2000 + case, 0, nq, d)
             if n > 3:
                 q[0] = db[3]
-            metrics = (oracle.L2, oracle.IP, oracle.COS) if dtype in FLOATS else (oracle.L2, oracle.IP)
-            for metric in metrics:
+            for metric in (oracle.L2, oracle.IP, oracle.COS):
                 ids, sc, isc = gs.search(q, k, metric=metric)
                 assert engine.profile_read()["last_path"] == 2, (case, dtype, n, d, nq, k)
                 qq = q.astype(np.float32) if dtype == oracle.F16 else q
@@ -200,7 +215,10 @@ def test_randomised_shapes_on_the_tensor_path(engine):
                         assert len(got) == kk
                         if dtype in (oracle.I8, oracle.U8):
                             assert np.array_equal(got, keep[o_ids[:kk].astype(np.int64)]), (case, metric, qi, got, keep[o_ids[:kk].astype(np.int64)])
-                            assert np.array_equal(isc[qi][:kk], o_isc[:kk])
+                            if metric != oracle.COS:
+                                assert np.array_equal(isc[qi][:kk], o_isc[:kk])
+                            else:
+                                assert np.array_equal(sc[qi][:kk].view(np.uint32), o_sc[:kk].view(np.uint32))
                         else:
                             if metric == oracle.L2:          # the tolerance is stated on d^2 (tests/util.py); near d = 0 the root amplifies it
                                 qn2 = float((qq[qi].astype(np.float64) ** 2).sum())

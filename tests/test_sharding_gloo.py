@@ -140,10 +140,10 @@ def test_every_rank_takes_the_same_scan_or_tensor_decision():
     assert mv.path_decision(2 * 4096, 2, 1, 2, 8, 10, 64) == (4096, True)
     assert mv.path_decision(2 * 4096 - 1, 2, 1, 2, 8, 10, 64) == (4095, False)
     assert mv.path_decision(8 * 4096 - 1, 8, 3, 0, 16, 10, 128) == (4095, False)
-    # what the tensor path does not take in auto mode: small batches, k > 512, integer cosine, Float32 rows beyond 1024 components
+    # what the tensor path does not take in auto mode: small batches, k > 512, Float32 rows beyond 1024 components
     assert mv.path_decision(10**8, 8, 1, 2, 3, 10, 768)[1] is False
     assert mv.path_decision(10**8, 8, 1, 2, 1024, 129, 768)[1] is True      # k up to 512 stays on the tensor path
     assert mv.path_decision(10**8, 8, 1, 2, 1024, 513, 768)[1] is False
-    assert mv.path_decision(10**8, 8, 3, 2, 1024, 10, 128)[1] is False
+    assert mv.path_decision(10**8, 8, 3, 2, 1024, 10, 128)[1] is True       # integer cosine: exact keys for the candidates
     assert mv.path_decision(10**6, 1, 0, 0, 1024, 10, 768)[1] is True
     assert mv.path_decision(10**6, 1, 0, 0, 1024, 10, 2048)[1] is False
