@@ -98,36 +98,30 @@ __device__ __forceinline__ void accum_float(const float* xf, const float* qf, fl
     }
 }
 
-// CTA epilogue shared by both scan shapes: sort each query's kScanWarps*k candidates, emit best k
-// ascending bitonic sort of one 64-bit word per lane, in registers
-__device__ __forceinline__ u64 warp_sort32(u64 v, int lane) {
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const u64 o = shfl_xor_u64(v, stride);
-            const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
-            v = take_min ? (o < v ? o : v) : (o > v ? o : v);
-        }
-    }
-    return v;
-}
-// k <= 32 (register lists): every warp sorts its own list with shuffles, then warp q merges the kScanWarps sorted lists
-// of query q by tournament straight into the CTA's output list: two block barriers instead of the 28 of a 128-word
-// block sort (the fixed cost of a search is what the small configs pay: a 256-row scan took 12.5 us).
+// CTA epilogue shared by both scan shapes: the best k of each query's kScanWarps*k candidates, ascending
+// k <= 32 (register lists): the kScanWarps * k candidates of a query are ranked by counting -- thread t holds candidate t
+// and counts the candidates that precede it (smaller word, or the same word at a lower position: the kInf fillers of a
+// list that never filled up), then stores it at its rank if that is below k.  No sort, no tournament rounds, one block
+// barrier between the warps' stores and the counting: the CTA epilogue is a fixed cost every search pays (it was a
+// shuffle sort per warp plus k rounds of a warp tournament; a 256-row search took 12.3 us).
 template <int NQ>
 __device__ __forceinline__ void emit_cta_lists_reg(const ScanParams& p, u64* lists, const u64 (&regl)[NQ], int lane, int warp) {
-    const int k = (int)p.k;
+    const uint32_t k = p.k, M = kScanWarps * k;
     __syncthreads();                                            // everybody is done with the query area / lists
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        const u64 v = warp_sort32(lane < k ? regl[q] : kInf, lane);
-        if (lane < k) lists[(size_t)q * p.P + warp * k + lane] = v;
-    }
+    for (int q = 0; q < NQ; q++)
+        if (lane < (int)k) lists[(size_t)q * p.P + warp * k + lane] = regl[q];
     __syncthreads();
-    for (int q = warp; q < NQ; q += kScanWarps) {
-        u64* out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
-        warp_tournament(lists + (size_t)q * p.P, (size_t)k, (uint32_t)kScanWarps, p.k, out, lane);
+    for (uint32_t idx = threadIdx.x; idx < NQ * M; idx += blockDim.x) {
+        const uint32_t q = idx / M, t = idx - q * M;
+        const u64* l = lists + (size_t)q * p.P;
+        const u64 c = l[t];
+        uint32_t rank = 0;
+        for (uint32_t u = 0; u < M; u++) {
+            const u64 o = l[u];
+            rank += (o < c || (o == c && u < t)) ? 1u : 0u;
+        }
+        if (rank < k) p.cand[((size_t)q * gridDim.x + blockIdx.x) * k + rank] = c;
     }
 }
 template <int NQ>
