@@ -163,8 +163,22 @@ __device__ __forceinline__ void fused_merge_tail(const ScanParams& p, const Scan
         __syncthreads();
         warp_tournament(cand_s + (size_t)l0 * k, k, nl, k, lvl1 + (size_t)warp * k, (int)lane);
         __syncthreads();
+        if (k <= 32) {
+            // second level by counting (like the CTA epilogue): kScanWarps * k candidates, one per thread
+            const uint32_t M = kScanWarps * k;
+            for (uint32_t t = threadIdx.x; t < M; t += blockDim.x) {
+                const u64 c = lvl1[t];
+                uint32_t rank = 0;
+                for (uint32_t u = 0; u < M; u++) {
+                    const u64 o = lvl1[u];
+                    rank += (o < c || (o == c && u < t)) ? 1u : 0u;
+                }
+                if (rank < k) cand_s[rank] = c;
+            }
+            __syncthreads();
+        }
         if (warp == 0) {
-            warp_tournament(lvl1, k, kScanWarps, k, cand_s, (int)lane);
+            if (k > 32) warp_tournament(lvl1, k, kScanWarps, k, cand_s, (int)lane);
             if (!tail.exchange) {
                 for (uint32_t j = lane; j < k; j += 32) emit_result(tail.mp, (uint32_t)q, j, cand_s[j]);
             } else {
