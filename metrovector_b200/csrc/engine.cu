@@ -505,7 +505,7 @@ struct SearchCtx {
 };
 
 // Phase 1: this shard's kernels and its local merge.  Without a communicator the local merge writes the final
-// outputs; with one it leaves nq*k packed candidates (global row ids applied) for the exchange.
+// outputs; with one it leaves nq*k packed candidates (row ids local to the shard) for the exchange.
 // Asynchronous on g->stream (except the finite check of device-resident float queries, see above).
 void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t nq, uint32_t kk, int metric, int qfinite,
                   uint64_t* d_ids, float* d_scores, int32_t* d_iscores, SearchCtx* ctx, bool final_here = true) {
@@ -602,7 +602,7 @@ void search_local(mvf_gpu_space* s, const void* d_queries, int qdtype, uint32_t 
     }
 }
 
-// Phase 2: the one exchange step -- every rank contributes its nq*k best (global ids already applied).  A group
+// Phase 2: the one exchange step (NCCL route) -- every rank contributes its nq*k best (shard-local row ids).  A group
 // engine brackets the members' calls with ncclGroupStart/End.
 void search_exchange(mvf_gpu_space* s, const SearchCtx& ctx) {
     mvf_gpu* g = s->g;

@@ -256,7 +256,7 @@ __device__ __forceinline__ void warp_tournament(const u64* base, size_t stride, 
 
 // X1 parameters (exchange_merge below; also the tail of a fused scan launch, scan_kernels.cuh)
 struct ExchangeParams {
-    const u64* mine;          // [nq][k] this rank's merged candidates (global row ids already applied)
+    const u64* mine;          // [nq][k] this rank's merged candidates (row ids local to its shard)
     uint4* const* peers;      // [world] window of rank r as mapped into this device (peers[rank] = window)
     uint4* window;            // this rank's own window
     uint32_t world, rank;
