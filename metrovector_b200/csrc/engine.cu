@@ -1,6 +1,7 @@
 // engine.cu -- the GPU engine behind the C ABI: residency (mmap -> HBM once per space, with row
 // norms), kernel dispatch for find_top_k_similar (examples/similarity_search.rs:140-176 of the
-// reference), and the row-sharded multi-GPU merge (one ncclAllGather of nq*k 64-bit candidates).
+// reference), and the row-sharded multi-GPU merge (one exchange of nq*k 64-bit candidates per rank: a peer-memory
+// kernel for small payloads, ncclAllGather above).
 // An engine is bound to one B200 (mvf_gpu_init; several processes then form a communicator with
 // mvf_gpu_comm_init) or, from ONE process, to several (mvf_gpu_init_multi: one member engine per device,
 // ncclCommInitAll, the same search phases driven device by device).  There is no CPU compute fallback:

@@ -2,11 +2,12 @@
 //   K0  row_norms        sqrt(sum x^2) and sum x^2 per row, once per resident space
 //   K1  scan_topk        distance + running top-k, one pass over the HBM-resident rows
 //   K3  merge_topk       per-query merge of candidate lists (per-CTA lists, or per-rank lists)
+//   X1  exchange_merge   cross-GPU exchange of the local top-k over peer memory + the merge, one kernel
 //   synth_fill           device-side synthetic rows (bench/tests)
 // What they replace: the loop body of find_top_k_similar, examples/similarity_search.rs:147-169
 // of the reference (get_vector -> as_f32 -> sum of squared differences -> heap push/pop).
-// Candidates are 64-bit words (order-preserving 32-bit key << 32 | 32-bit row id), so "smallest
-// score, lowest index on ties" is plain unsigned order everywhere.
+// Candidates are 64-bit words (order-preserving 32-bit key << 32 | 32-bit row id inside the shard), so
+// "smallest score, lowest index on ties" is plain unsigned order everywhere.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
