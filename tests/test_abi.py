@@ -45,3 +45,21 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_example_program_builds_against_the_abi_only(tmp_path):
+    # examples/similarity_search.cpp is the drop-in for the reference's example program: it may include nothing but
+    # include/mvf_b200.h (+ the C++ host header) and must link against the shared library alone
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++ on this box")
+    out = tmp_path / "similarity_search"
+    cmd = [cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "similarity_search.cpp"),
+           "-L" + os.path.join(ROOT, "metrovector_b200"), "-l:libmvf_b200.so", "-Wl,-rpath," + os.path.join(ROOT, "metrovector_b200"),
+           "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    src = open(os.path.join(ROOT, "examples", "similarity_search.cpp")).read()
+    assert "oracle" not in src and "cuda_runtime" not in src
