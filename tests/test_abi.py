@@ -47,19 +47,29 @@ def test_product_does_not_touch_the_oracle():
                 assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
 
 
-def test_example_program_builds_against_the_abi_only(tmp_path):
-    # examples/similarity_search.cpp is the drop-in for the reference's example program: it may include nothing but
-    # include/mvf_b200.h (+ the C++ host header) and must link against the shared library alone
+@pytest.mark.parametrize("example", ["similarity_search", "simple"])
+def test_example_programs_build_against_the_abi_only(tmp_path, example):
+    # examples/*.cpp are the drop-ins for the reference's two example programs (examples/similarity_search.rs,
+    # examples/simple.rs): they include nothing but include/mvf_b200.h and link against the shared library alone
     import shutil
     import subprocess
     cxx = shutil.which("g++")
     if cxx is None:
         pytest.skip("no g++ on this box")
-    out = tmp_path / "similarity_search"
-    cmd = [cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "similarity_search.cpp"),
+    out = tmp_path / example
+    cmd = [cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", example + ".cpp"),
            "-L" + os.path.join(ROOT, "metrovector_b200"), "-l:libmvf_b200.so", "-Wl,-rpath," + os.path.join(ROOT, "metrovector_b200"),
            "-o", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
-    src = open(os.path.join(ROOT, "examples", "similarity_search.cpp")).read()
+    src = open(os.path.join(ROOT, "examples", example + ".cpp")).read()
     assert "oracle" not in src and "cuda_runtime" not in src
+    if example == "simple":
+        # without a GPU the host steps (build, read back, print the rows) run and the search step fails loudly
+        import torch
+        run = subprocess.run([str(out)], capture_output=True, text=True, timeout=120)
+        assert "Vector 4: [1.0, 3.0, 5.0, 7.0]" in run.stdout and "Total vectors: 5" in run.stdout
+        if not torch.cuda.is_available():
+            assert run.returncode != 0 and "no CPU fallback" in run.stderr
+        else:
+            assert run.returncode == 0 and "Best match: Vector 3 (distance: 1.00)" in run.stdout
